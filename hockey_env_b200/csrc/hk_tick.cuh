@@ -1,0 +1,124 @@
+// hk_tick.cuh -- one full env tick as the kernels run it: policy -> step -> info/reward ->
+// outputs -> auto-reset.  This is the body of HockeyEnv.step / HockeyEnv_BasicOpponent.step
+// (reference hockey_env.py:658-695, :882-886) plus the batched API's auto-reset.
+#pragma once
+#include "hk_state.cuh"
+
+namespace hk {
+
+struct StepIO {
+  const float* action;  // [n, stride] or null
+  int stride;
+  int pol1, pol2, flags;
+  float* obs;        // [n,18]
+  float* obs2;       // [n,18] or null
+  float* reward;     // [n] or null
+  float* reward2;    // [n] or null
+  uint8_t* done;     // [n] or null
+  float* info;       // [n,4] or null
+  float* info2;      // [n,4] or null
+  float* final_obs;  // [n,18] or null
+};
+
+struct TickStats {
+  int episodes, wins, losses, draws, steps, len, touch1, touch2, velIters, toi, overflow;
+  double ret1, ret2, ret1sq;
+};
+HK_HD void tickStatsZero(TickStats& s) {
+  s.episodes = s.wins = s.losses = s.draws = s.steps = s.len = s.touch1 = s.touch2 = s.velIters = s.toi = s.overflow = 0;
+  s.ret1 = s.ret2 = s.ret1sq = 0.0;
+}
+
+HK_HD void writeRow18(float* dst, const float* o) {
+  // rows are 72 B: 8-byte aligned, so 9 float2 stores
+  for (int k = 0; k < 9; ++k) {
+#if defined(__CUDA_ARCH__)
+    reinterpret_cast<float2*>(dst)[k] = make_float2(o[2 * k], o[2 * k + 1]);
+#else
+    dst[2 * k] = o[2 * k];
+    dst[2 * k + 1] = o[2 * k + 1];
+#endif
+  }
+}
+
+// `write` = false suppresses all per-tick outputs (fused rollout, all but the last tick)
+HK_HD void envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e, uint64_t env_id, size_t i,
+                   const StepIO& io, bool write, TickStats& st) {
+  float a[8];
+  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+  const int had1 = e.has1, had2 = e.has2;
+  envStep(S, cfg, cache, e, a);
+  double inf[4], inf2[4];
+  getInfo(cfg, e, false, inf);
+  getInfo(cfg, e, true, inf2);
+  const double cr = computeReward(e);
+  const double r = cr + inf[1];
+  const double r2 = -cr + inf2[1];
+  e.ret[0] += r;
+  e.ret[1] += r2;
+  st.steps += 1;
+  st.velIters += (int)e.nVelIters;
+  st.toi += (int)e.nToiEvents;
+  st.overflow += (int)e.nOverflow;
+  e.nVelIters = e.nToiEvents = e.nOverflow = 0;
+  if (e.has1 == HK_MAX_TIME_KEEP_PUCK && had1 != HK_MAX_TIME_KEEP_PUCK) st.touch1 += 1;
+  if (e.has2 == HK_MAX_TIME_KEEP_PUCK && had2 != HK_MAX_TIME_KEEP_PUCK) st.touch2 += 1;
+  if (write) {
+    if (io.reward) io.reward[i] = (float)r;
+    if (io.reward2) io.reward2[i] = (float)r2;
+    if (io.done) io.done[i] = e.done ? 1 : 0;
+    if (io.info) {
+      float* q = io.info + 4 * i;
+      q[0] = (float)inf[0]; q[1] = (float)inf[1]; q[2] = (float)inf[2]; q[3] = (float)inf[3];
+    }
+    if (io.info2) {
+      float* q = io.info2 + 4 * i;
+      q[0] = (float)inf2[0]; q[1] = (float)inf2[1]; q[2] = (float)inf2[2]; q[3] = (float)inf2[3];
+    }
+    if (io.final_obs) {
+      float o[18];
+      getObs(e, o);
+      writeRow18(io.final_obs + 18 * i, o);
+    }
+  }
+  if (e.done && (io.flags & 1)) {
+    st.episodes += 1;
+    if (e.winner == 1) st.wins += 1;
+    else if (e.winner == -1) st.losses += 1;
+    else st.draws += 1;
+    st.ret1 += e.ret[0];
+    st.ret2 += e.ret[1];
+    st.ret1sq += e.ret[0] * e.ret[0];
+    st.len += e.time;
+    envReset(S, cfg, e, env_id, -1);
+  }
+  if (write) {
+    float o[18];
+    if (io.obs) {
+      getObs(e, o);
+      writeRow18(io.obs + 18 * i, o);
+    }
+    if (io.obs2) {
+      getObs2(e, o);
+      writeRow18(io.obs2 + 18 * i, o);
+    }
+  }
+}
+
+// HockeyEnv.__init__ for one env (hockey_env.py:91-155): phases of the built-in controllers
+// (BasicOpponent.__init__, :785), then reset(one_starting=True)
+HK_HD void envCreate(const Scene& S, const Config& cfg, Env& e, uint64_t env_id) {
+  e.has1 = e.has2 = 0;
+  e.one_starts = true;
+  e.episode = 0;
+  e.tick = 0;
+  e.nVelIters = e.nToiEvents = e.nOverflow = 0;
+  e.enabled = 0xFFFFFFFFu;
+  e.nmf = 0;
+  U4 r = philox(cfg.seed, env_id, 0, HK_STREAM_PHASE0);
+  e.phase[0] = 0.0 + (3.14159265358979323846 - 0.0) * u53(r.x, r.y);
+  e.phase[1] = 0.0 + (3.14159265358979323846 - 0.0) * u53(r.z, r.w);
+  envReset(S, cfg, e, env_id, 1);
+}
+
+}  // namespace hk

@@ -1,0 +1,1076 @@
+// hk_world.cuh -- one env's world step: Collide -> island solve -> SolveTOI, specialised to the fixed
+// HockeyEnv scene (3 dynamic bodies, 10 static fixtures, 27 candidate pairs).
+//
+// Replaces `self.world.Step(self.timeStep, 6 * 30, 2 * 30)` (reference hockey_env.py:682) and the
+// ContactDetector callbacks it fires (hockey_env.py:50-73).  B200-first restructuring relative to
+// a general engine:
+//   * no dynamic tree / pair hash: the broad phase is three fat AABBs per env tested against a
+//     constant table; the set of live contacts is one 64-bit packed list (newest first, the order
+//     Box2D's contact list would have) plus 27-bit masks;
+//   * no heap, no pointers between bodies: 3 dynamic bodies live in registers / local memory,
+//     statics are rows of the constant Scene;
+//   * the 180 velocity iterations stop as soon as one full Gauss-Seidel sweep applies only zero
+//     impulses -- from then on every later sweep is bit-identical, so the result equals running
+//     all 180 (checked against the oracle, which always runs 180);
+//   * warm-start impulses live in a lazily touched global cache, not in the per-step state record.
+#pragma once
+#include "hk_collide.cuh"
+
+namespace hk {
+
+enum { MAX_MANIFOLDS = 8, MAX_CLIST = 12 };
+
+struct Body {
+  V2 p;   // m_xf.p (body origin)
+  Rot q;  // m_xf.q
+  V2 c0, c;
+  float a0, a, alpha0;
+  V2 v;
+  float w;
+  V2 f;
+  float tq;
+  float ldamp, adamp, sleep;
+  bool awake, island;
+};
+
+// persistent warm-start cache: 6 words per pair (key0,key1,ni0,ti0,ni1,ti1), strided over envs
+struct Cache {
+  uint32_t* base;  // already offset to this env
+  size_t stride;   // in words, between consecutive (pair,word) slots
+  HK_HD uint32_t& at(int pid, int k) const { return base[(size_t)(pid * 6 + k) * stride]; }
+};
+HK_HD float u2f(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+HK_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u;
+#endif
+}
+
+struct Env {
+  Body b[3];
+  int has1, has2, time, winner;
+  bool done, one_starts;
+  AABB fat[3];
+  uint32_t moved;  // bit0-2: buffered proxy moves (r1, r2, puck); bit3: new fixtures since last step
+  double phase[2];
+  uint32_t episode, tick;
+  double ret[2];
+  uint64_t clist;  // packed live-contact list, 5 bits per pair id, entry 0 = newest
+  int ncontacts;
+  uint32_t exist, touch;  // 27-bit masks
+  uint64_t pcount;        // 2 bits per pair: manifold point count held in the cache
+  // per-step scratch
+  uint32_t enabled;
+  Manifold mf[MAX_MANIFOLDS];
+  int mfPid[MAX_MANIFOLDS];
+  int nmf;
+  // counters (statistics)
+  uint32_t nVelIters, nToiEvents, nOverflow;
+};
+
+struct Config {
+  int mode, keep_mode, max_timesteps;
+  uint64_t seed;
+};
+
+HK_HD int clistGet(uint64_t l, int i) { return (int)((l >> (5 * i)) & 31u); }
+HK_HD int getCount(const Env& e, int pid) { return (int)((e.pcount >> (2 * pid)) & 3u); }
+HK_HD void setCount(Env& e, int pid, int n) {
+  e.pcount = (e.pcount & ~((uint64_t)3 << (2 * pid))) | ((uint64_t)n << (2 * pid));
+}
+HK_HD void clistRemoveAt(Env& e, int i) {
+  uint64_t lowMask = ((uint64_t)1 << (5 * i)) - 1;
+  uint64_t low = e.clist & lowMask;
+  uint64_t high = (i + 1 < MAX_CLIST + 1) ? (e.clist >> (5 * (i + 1))) : 0;
+  e.clist = low | (high << (5 * i));
+  e.ncontacts--;
+}
+HK_HD void clistPushHead(Env& e, int pid) {
+  if (e.ncontacts == MAX_CLIST) {  // cannot happen in this scene; counted, never silent
+    int last = clistGet(e.clist, MAX_CLIST - 1);
+    e.exist &= ~(1u << last);
+    e.touch &= ~(1u << last);
+    setCount(e, last, 0);
+    clistRemoveAt(e, MAX_CLIST - 1);
+    e.nOverflow++;
+  }
+  e.clist = (e.clist << 5) | (uint64_t)pid;
+  e.ncontacts++;
+}
+
+HK_HD void setAwake(Body& b, bool flag) {
+  if (flag) {
+    if (!b.awake) {
+      b.awake = true;
+      b.sleep = 0.0f;
+    }
+  } else {
+    b.awake = false;
+    b.sleep = 0.0f;
+    b.v = mk(0.0f, 0.0f);
+    b.w = 0.0f;
+    b.f = mk(0.0f, 0.0f);
+    b.tq = 0.0f;
+  }
+}
+HK_HD void applyForceToCenter(Body& b, V2 f) {  // wake = True at every reference call site
+  if (!b.awake) setAwake(b, true);
+  b.f += f;
+}
+HK_HD void applyTorque(Body& b, float t) {
+  if (!b.awake) setAwake(b, true);
+  b.tq += t;
+}
+HK_HD void setLinearVelocity(Body& b, V2 v) {
+  if (dot(v, v) > 0.0f) setAwake(b, true);
+  b.v = v;
+}
+HK_HD void syncTransform(const Scene& S, Body& b, int bi) {
+  b.q = rotOf(b.a);
+  b.p = b.c - mul(b.q, mk(S.lcx[bi], S.lcy[bi]));
+}
+HK_HD Xf bodyXf(const Body& b) {
+  Xf x;
+  x.p = b.p;
+  x.q = b.q;
+  return x;
+}
+HK_HD Xf staticXf(const Scene& S, int f) {
+  Xf x;
+  x.p = mk(S.spx[f], S.spy[f]);
+  x.q.s = 0.0f;
+  x.q.c = 1.0f;
+  return x;
+}
+HK_HD Xf fixtureXf(const Scene& S, const Env& e, int f) { return f < N_STATIC_FIX ? staticXf(S, f) : bodyXf(e.b[f - F_R1]); }
+HK_HD AABB fixtureFat(const Scene& S, const Env& e, int f) { return f < N_STATIC_FIX ? S.sfat[f] : e.fat[f - F_R1]; }
+HK_HD int staticBodyOf(int f) { return f < 6 ? f : (f < 8 ? 6 : 7); }
+
+// ---- fixture AABB / broad-phase proxy (b2Fixture::Synchronize, b2DynamicTree::MoveProxy) ----------
+HK_HD AABB shapeAABB(const Scene& S, int bi, const Xf& xf) {
+  AABB r;
+  if (bi == B_PUCK) {
+    float rad = S.puckRadius;
+    V2 pp = xf.p + mul(xf.q, mk(0.0f, 0.0f));
+    r.lx = pp.x - rad;
+    r.ly = pp.y - rad;
+    r.hx = pp.x + rad;
+    r.hy = pp.y + rad;
+    return r;
+  }
+  const Poly& P = S.poly[F_R1 + bi];
+  V2 lower = mul(xf, polyV(P, 0)), upper = lower;
+  for (int i = 1; i < P.count; ++i) {
+    V2 v = mul(xf, polyV(P, i));
+    lower = mk(fmin2(lower.x, v.x), fmin2(lower.y, v.y));
+    upper = mk(fmax2(upper.x, v.x), fmax2(upper.y, v.y));
+  }
+  r.lx = lower.x - HK_POLYGON_RADIUS;
+  r.ly = lower.y - HK_POLYGON_RADIUS;
+  r.hx = upper.x + HK_POLYGON_RADIUS;
+  r.hy = upper.y + HK_POLYGON_RADIUS;
+  return r;
+}
+HK_HD void moveProxy(Env& e, int bi, const AABB& aabb, V2 displacement) {
+  if (aabbContains(e.fat[bi], aabb)) return;
+  AABB b = aabb;
+  b.lx = b.lx - HK_AABB_EXTENSION;
+  b.ly = b.ly - HK_AABB_EXTENSION;
+  b.hx = b.hx + HK_AABB_EXTENSION;
+  b.hy = b.hy + HK_AABB_EXTENSION;
+  V2 d = HK_AABB_MULTIPLIER * displacement;
+  if (d.x < 0.0f) b.lx += d.x; else b.hx += d.x;
+  if (d.y < 0.0f) b.ly += d.y; else b.hy += d.y;
+  e.fat[bi] = b;
+  e.moved |= 1u << bi;
+}
+HK_HD void synchronizeFixtures(const Scene& S, Env& e, int bi) {
+  Body& b = e.b[bi];
+  Xf xf1;
+  xf1.q = rotOf(b.a0);
+  xf1.p = b.c0 - mul(xf1.q, mk(S.lcx[bi], S.lcy[bi]));
+  AABB a1 = shapeAABB(S, bi, xf1);
+  AABB a2 = shapeAABB(S, bi, bodyXf(b));
+  AABB comb;
+  comb.lx = fmin2(a1.lx, a2.lx);
+  comb.ly = fmin2(a1.ly, a2.ly);
+  comb.hx = fmax2(a1.hx, a2.hx);
+  comb.hy = fmax2(a1.hy, a2.hy);
+  moveProxy(e, bi, comb, b.p - xf1.p);
+}
+// b2Body::SetTransform (puck teleport, hockey_env.py:619)
+HK_HD void setTransformPuck(const Scene& S, Env& e, V2 position) {
+  Body& b = e.b[B_PUCK];
+  b.q = rotOf(b.a);
+  b.p = position;
+  b.c = mul(bodyXf(b), mk(S.lcx[B_PUCK], S.lcy[B_PUCK]));
+  b.c0 = b.c;
+  b.a0 = b.a;
+  AABB a1 = shapeAABB(S, B_PUCK, bodyXf(b));
+  AABB comb;
+  comb.lx = fmin2(a1.lx, a1.lx);
+  comb.ly = fmin2(a1.ly, a1.ly);
+  comb.hx = fmax2(a1.hx, a1.hx);
+  comb.hy = fmax2(a1.hy, a1.hy);
+  moveProxy(e, B_PUCK, comb, b.p - b.p);
+}
+
+// b2ContactManager::FindNewContacts for the buffered proxy moves
+HK_HD void findNewContacts(const Scene& S, Env& e) {
+  uint32_t mv = e.moved & 7u;
+  e.moved &= ~7u;
+  if (!mv) return;
+  uint32_t cand = 0;
+  if (mv & 1u) cand |= HK_PAIRS_R1;
+  if (mv & 2u) cand |= HK_PAIRS_R2;
+  if (mv & 4u) cand |= HK_PAIRS_PUCK;
+  cand &= ~e.exist;
+  uint32_t fresh = 0;
+  for (int pid = 0; pid < N_PAIRS; ++pid) {
+    if (!((cand >> pid) & 1u)) continue;
+    int fA = S.pairFA[pid], fB = S.pairFB[pid];
+    if (aabbOverlap(fixtureFat(S, e, fA), fixtureFat(S, e, fB))) fresh |= 1u << pid;
+  }
+  if (!fresh) return;
+  for (int k = 0; k < N_PAIRS; ++k) {  // creation order = sorted (proxyA, proxyB); each goes to the list head
+    int pid = S.sortedPairs[k];
+    if (!((fresh >> pid) & 1u)) continue;
+    clistPushHead(e, pid);
+    e.exist |= 1u << pid;
+    e.touch &= ~(1u << pid);
+    e.enabled |= 1u << pid;
+    setCount(e, pid, 0);
+    if (!((HK_PAIRS_SENSOR >> pid) & 1u)) {
+      int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
+      if (bA >= 0) setAwake(e.b[bA], true);
+      if (bB >= 0) setAwake(e.b[bB], true);
+    }
+  }
+}
+
+// ---- ContactDetector.BeginContact (hockey_env.py:50-73) --------------------------------------------
+HK_HD void beginContact(const Config& cfg, Env& e, int pid) {
+  if (pid == 24) {  // puck x goal_player_2
+    e.done = true;
+    e.winner = 1;
+  } else if (pid == 23) {  // puck x goal_player_1
+    e.done = true;
+    e.winner = -1;
+  } else if (pid == 25) {
+    if (cfg.keep_mode && (double)e.b[B_PUCK].v.x < 0.1) {
+      if (e.has1 == 0) e.has1 = 15;
+    }
+  } else if (pid == 26) {
+    if (cfg.keep_mode && (double)e.b[B_PUCK].v.x > -0.1) {
+      if (e.has2 == 0) e.has2 = 15;
+    }
+  }
+}
+
+HK_HD int findSlot(const Env& e, int pid) {
+  for (int i = 0; i < e.nmf; ++i)
+    if (e.mfPid[i] == pid) return i;
+  return -1;
+}
+
+HK_HD void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
+  int fA = S.pairFA[pid], fB = S.pairFB[pid];
+  Xf xfA = fixtureXf(S, e, fA);
+  if (fB == F_PUCK) {
+    collidePolygonCircle(m, S.poly[fA], xfA, e.b[B_PUCK].p, S.puckRadius);
+  } else {
+    collidePolygons(m, S.poly[fA], xfA, S.poly[fB], bodyXf(e.b[fB - F_R1]));
+  }
+}
+
+// b2Contact::Update
+HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, Env& e, int pid) {
+  const uint32_t bit = 1u << pid;
+  e.enabled |= bit;
+  const bool wasTouching = (e.touch & bit) != 0;
+  bool touching;
+  if ((HK_PAIRS_SENSOR >> pid) & 1u) {
+    int fA = S.pairFA[pid];
+    touching = testOverlapPolyPuck(S.poly[fA], staticXf(S, fA), e.b[B_PUCK].p, S.puckRadius);
+  } else {
+    int slot = findSlot(e, pid);
+    Manifold tmp;
+    evaluateManifold(S, e, pid, &tmp);
+    touching = tmp.count > 0;
+    int oldCount = getCount(e, pid);
+    uint32_t oldKey[2] = {0, 0};
+    float oldNi[2] = {0, 0}, oldTi[2] = {0, 0};
+    for (int j = 0; j < oldCount; ++j) {
+      oldKey[j] = cache.at(pid, j);
+      oldNi[j] = u2f(cache.at(pid, 2 + 2 * j));
+      oldTi[j] = u2f(cache.at(pid, 3 + 2 * j));
+    }
+    for (int i = 0; i < tmp.count; ++i) {
+      tmp.ni[i] = 0.0f;
+      tmp.ti[i] = 0.0f;
+      for (int j = 0; j < oldCount; ++j) {
+        if (oldKey[j] == tmp.key[i]) {
+          tmp.ni[i] = oldNi[j];
+          tmp.ti[i] = oldTi[j];
+          break;
+        }
+      }
+    }
+    for (int i = 0; i < tmp.count; ++i) {
+      cache.at(pid, i) = tmp.key[i];
+      cache.at(pid, 2 + 2 * i) = f2u(tmp.ni[i]);
+      cache.at(pid, 3 + 2 * i) = f2u(tmp.ti[i]);
+    }
+    setCount(e, pid, tmp.count);
+    if (touching) {
+      if (slot < 0) {
+        if (e.nmf < MAX_MANIFOLDS) {
+          slot = e.nmf++;
+        } else {
+          slot = MAX_MANIFOLDS - 1;  // cannot happen in this scene; counted
+          e.nOverflow++;
+        }
+        e.mfPid[slot] = pid;
+      }
+      e.mf[slot] = tmp;
+    } else if (slot >= 0) {
+      e.mf[slot].count = 0;
+    }
+    if (touching != wasTouching) {
+      int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
+      if (bA >= 0) setAwake(e.b[bA], true);
+      if (bB >= 0) setAwake(e.b[bB], true);
+    }
+  }
+  if (touching) e.touch |= bit; else e.touch &= ~bit;
+  if (!wasTouching && touching) beginContact(cfg, e, pid);
+}
+
+// b2ContactManager::Collide
+HK_HD void collide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
+  int i = 0;
+  while (i < e.ncontacts) {
+    int pid = clistGet(e.clist, i);
+    int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
+    bool activeA = bA >= 0 && e.b[bA].awake;
+    bool activeB = bB >= 0 && e.b[bB].awake;
+    if (!activeA && !activeB) {
+      ++i;
+      continue;
+    }
+    if (!aabbOverlap(fixtureFat(S, e, S.pairFA[pid]), fixtureFat(S, e, S.pairFB[pid]))) {
+      clistRemoveAt(e, i);
+      e.exist &= ~(1u << pid);
+      e.touch &= ~(1u << pid);
+      setCount(e, pid, 0);
+      continue;
+    }
+    updateContact(S, cfg, cache, e, pid);
+    ++i;
+  }
+}
+
+// ---- contact solver (b2ContactSolver) ---------------------------------------------------------------
+struct VCPoint {
+  V2 rA, rB;
+  float ni, ti, normalMass, tangentMass, bias;
+};
+struct VC {
+  VCPoint pt[2];
+  V2 normal;
+  float k11, k12, k22;          // K
+  float n11, n12, n21, n22;     // normalMass = K^-1  (ex.x, ey.x, ex.y, ey.y)
+  float mA, iA, mB, iB, friction, restitution;
+  int bA, bB;  // dynamic body index or -1
+  int count, slot;
+};
+
+HK_HD void worldManifold(const Manifold& m, const Xf& xfA, float radiusA, const Xf& xfB, float radiusB, V2* normal,
+                         V2 points[2]) {
+  if (m.type == MANIFOLD_FACE_A) {
+    *normal = mul(xfA.q, m.localNormal);
+    V2 planePoint = mul(xfA, m.localPoint);
+    for (int i = 0; i < m.count; ++i) {
+      V2 clipPoint = mul(xfB, m.lp[i]);
+      V2 cA = clipPoint + (radiusA - dot(clipPoint - planePoint, *normal)) * (*normal);
+      V2 cB = clipPoint - radiusB * (*normal);
+      points[i] = 0.5f * (cA + cB);
+    }
+  } else {
+    *normal = mul(xfB.q, m.localNormal);
+    V2 planePoint = mul(xfB, m.localPoint);
+    for (int i = 0; i < m.count; ++i) {
+      V2 clipPoint = mul(xfA, m.lp[i]);
+      V2 cB = clipPoint + (radiusB - dot(clipPoint - planePoint, *normal)) * (*normal);
+      V2 cA = clipPoint - radiusA * (*normal);
+      points[i] = 0.5f * (cA + cB);
+    }
+    *normal = -(*normal);
+  }
+}
+
+struct BodyRef {  // position/velocity view of one side of a constraint (static => zeros, fixed pose)
+  V2 c;
+  float a;
+  V2 v;
+  float w;
+  V2 lc;
+};
+HK_HD BodyRef bodyRef(const Scene& S, const Env& e, int fixture) {
+  BodyRef r;
+  if (fixture < N_STATIC_FIX) {
+    r.c = mk(S.spx[fixture], S.spy[fixture]);
+    r.a = 0.0f;
+    r.v = mk(0.0f, 0.0f);
+    r.w = 0.0f;
+    r.lc = mk(0.0f, 0.0f);
+  } else {
+    int bi = fixture - F_R1;
+    r.c = e.b[bi].c;
+    r.a = e.b[bi].a;
+    r.v = e.b[bi].v;
+    r.w = e.b[bi].w;
+    r.lc = mk(S.lcx[bi], S.lcy[bi]);
+  }
+  return r;
+}
+HK_HD float fixtureRadius(const Scene& S, int f) { return f == F_PUCK ? S.puckRadius : HK_POLYGON_RADIUS; }
+
+// b2ContactSolver ctor + InitializeVelocityConstraints for one contact
+HK_HD void initConstraint(const Scene& S, const Env& e, int pid, int slot, bool warmStarting, VC* vc) {
+  const Manifold& m = e.mf[slot];
+  int fA = S.pairFA[pid], fB = S.pairFB[pid];
+  vc->slot = slot;
+  vc->bA = fixtureBody(fA);
+  vc->bB = fixtureBody(fB);
+  vc->mA = vc->bA >= 0 ? S.invMass[vc->bA] : 0.0f;
+  vc->iA = vc->bA >= 0 ? S.invI[vc->bA] : 0.0f;
+  vc->mB = vc->bB >= 0 ? S.invMass[vc->bB] : 0.0f;
+  vc->iB = vc->bB >= 0 ? S.invI[vc->bB] : 0.0f;
+  vc->friction = S.friction[pid];
+  vc->restitution = S.restitution[pid];
+  vc->count = m.count;
+  const float dtRatio = 1.0f;
+  for (int j = 0; j < m.count; ++j) {
+    vc->pt[j].ni = warmStarting ? dtRatio * m.ni[j] : 0.0f;
+    vc->pt[j].ti = warmStarting ? dtRatio * m.ti[j] : 0.0f;
+  }
+  BodyRef A = bodyRef(S, e, fA), B = bodyRef(S, e, fB);
+  float mA = vc->mA, mB = vc->mB, iA = vc->iA, iB = vc->iB;
+  Xf xfA, xfB;
+  xfA.q = rotOf(A.a);
+  xfB.q = rotOf(B.a);
+  xfA.p = A.c - mul(xfA.q, A.lc);
+  xfB.p = B.c - mul(xfB.q, B.lc);
+  V2 points[2];
+  worldManifold(m, xfA, fixtureRadius(S, fA), xfB, fixtureRadius(S, fB), &vc->normal, points);
+  for (int j = 0; j < vc->count; ++j) {
+    VCPoint* p = vc->pt + j;
+    p->rA = points[j] - A.c;
+    p->rB = points[j] - B.c;
+    float rnA = cross(p->rA, vc->normal);
+    float rnB = cross(p->rB, vc->normal);
+    float kNormal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    p->normalMass = kNormal > 0.0f ? 1.0f / kNormal : 0.0f;
+    V2 tangent = cross(vc->normal, 1.0f);
+    float rtA = cross(p->rA, tangent);
+    float rtB = cross(p->rB, tangent);
+    float kTangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+    p->tangentMass = kTangent > 0.0f ? 1.0f / kTangent : 0.0f;
+    p->bias = 0.0f;
+    float vRel = dot(vc->normal, B.v + cross(B.w, p->rB) - A.v - cross(A.w, p->rA));
+    if (vRel < -HK_VELOCITY_THRESHOLD) p->bias = -vc->restitution * vRel;
+  }
+  if (vc->count == 2) {
+    VCPoint* p1 = vc->pt + 0;
+    VCPoint* p2 = vc->pt + 1;
+    float rn1A = cross(p1->rA, vc->normal);
+    float rn1B = cross(p1->rB, vc->normal);
+    float rn2A = cross(p2->rA, vc->normal);
+    float rn2B = cross(p2->rB, vc->normal);
+    float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+    float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+    float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+    const float k_maxConditionNumber = 1000.0f;
+    if (k11 * k11 < k_maxConditionNumber * (k11 * k22 - k12 * k12)) {
+      vc->k11 = k11;
+      vc->k12 = k12;
+      vc->k22 = k22;
+      float a = k11, b = k12, c = k12, d = k22;
+      float det = a * d - b * c;
+      if (det != 0.0f) det = 1.0f / det;
+      vc->n11 = det * d;
+      vc->n12 = -det * b;
+      vc->n21 = -det * c;
+      vc->n22 = det * a;
+    } else {
+      vc->count = 1;
+    }
+  }
+}
+
+struct Vel {
+  V2 v;
+  float w;
+};
+HK_HD Vel loadVel(const Env& e, int bi) {
+  Vel r;
+  if (bi >= 0) {
+    r.v = e.b[bi].v;
+    r.w = e.b[bi].w;
+  } else {
+    r.v = mk(0.0f, 0.0f);
+    r.w = 0.0f;
+  }
+  return r;
+}
+HK_HD void storeVel(Env& e, int bi, const Vel& x) {
+  if (bi >= 0) {
+    e.b[bi].v = x.v;
+    e.b[bi].w = x.w;
+  }
+}
+
+HK_HD void warmStartConstraint(Env& e, const VC& vc) {
+  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
+  V2 normal = vc.normal;
+  V2 tangent = cross(normal, 1.0f);
+  for (int j = 0; j < vc.count; ++j) {
+    const VCPoint& p = vc.pt[j];
+    V2 P = p.ni * normal + p.ti * tangent;
+    A.w -= vc.iA * cross(p.rA, P);
+    A.v -= vc.mA * P;
+    B.w += vc.iB * cross(p.rB, P);
+    B.v += vc.mB * P;
+  }
+  storeVel(e, vc.bA, A);
+  storeVel(e, vc.bB, B);
+}
+
+// one Gauss-Seidel pass over one contact; returns true if any applied impulse increment was non-zero
+HK_HD bool solveVelocityConstraint(Env& e, VC& vc) {
+  bool changed = false;
+  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
+  const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
+  V2 vA = A.v, vB = B.v;
+  float wA = A.w, wB = B.w;
+  V2 normal = vc.normal;
+  V2 tangent = cross(normal, 1.0f);
+  float friction = vc.friction;
+  for (int j = 0; j < vc.count; ++j) {
+    VCPoint* p = vc.pt + j;
+    V2 dv = vB + cross(wB, p->rB) - vA - cross(wA, p->rA);
+    float vt = dot(dv, tangent) - 0.0f;
+    float lambda = p->tangentMass * (-vt);
+    float maxFriction = friction * p->ni;
+    float newImpulse = fclamp(p->ti + lambda, -maxFriction, maxFriction);
+    lambda = newImpulse - p->ti;
+    p->ti = newImpulse;
+    changed = changed || (lambda != 0.0f);
+    V2 P = lambda * tangent;
+    vA -= mA * P;
+    wA -= iA * cross(p->rA, P);
+    vB += mB * P;
+    wB += iB * cross(p->rB, P);
+  }
+  if (vc.count == 1) {
+    VCPoint* p = vc.pt + 0;
+    V2 dv = vB + cross(wB, p->rB) - vA - cross(wA, p->rA);
+    float vn = dot(dv, normal);
+    float lambda = -p->normalMass * (vn - p->bias);
+    float newImpulse = fmax2(p->ni + lambda, 0.0f);
+    lambda = newImpulse - p->ni;
+    p->ni = newImpulse;
+    changed = changed || (lambda != 0.0f);
+    V2 P = lambda * normal;
+    vA -= mA * P;
+    wA -= iA * cross(p->rA, P);
+    vB += mB * P;
+    wB += iB * cross(p->rB, P);
+  } else {
+    VCPoint* cp1 = vc.pt + 0;
+    VCPoint* cp2 = vc.pt + 1;
+    V2 a = mk(cp1->ni, cp2->ni);
+    V2 dv1 = vB + cross(wB, cp1->rB) - vA - cross(wA, cp1->rA);
+    V2 dv2 = vB + cross(wB, cp2->rB) - vA - cross(wA, cp2->rA);
+    float vn1 = dot(dv1, normal);
+    float vn2 = dot(dv2, normal);
+    V2 b;
+    b.x = vn1 - cp1->bias;
+    b.y = vn2 - cp2->bias;
+    b -= mk(vc.k11 * a.x + vc.k12 * a.y, vc.k12 * a.x + vc.k22 * a.y);
+    V2 x;
+    bool found = false;
+    // case 1
+    x = -mk(vc.n11 * b.x + vc.n12 * b.y, vc.n21 * b.x + vc.n22 * b.y);
+    if (x.x >= 0.0f && x.y >= 0.0f) found = true;
+    if (!found) {  // case 2
+      x.x = -cp1->normalMass * b.x;
+      x.y = 0.0f;
+      vn2 = vc.k12 * x.x + b.y;
+      if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
+    }
+    if (!found) {  // case 3
+      x.x = 0.0f;
+      x.y = -cp2->normalMass * b.y;
+      vn1 = vc.k12 * x.y + b.x;
+      if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
+    }
+    if (!found) {  // case 4
+      x.x = 0.0f;
+      x.y = 0.0f;
+      vn1 = b.x;
+      vn2 = b.y;
+      if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
+    }
+    if (found) {
+      V2 d = x - a;
+      V2 P1 = d.x * normal, P2 = d.y * normal;
+      vA -= mA * (P1 + P2);
+      wA -= iA * (cross(cp1->rA, P1) + cross(cp2->rA, P2));
+      vB += mB * (P1 + P2);
+      wB += iB * (cross(cp1->rB, P1) + cross(cp2->rB, P2));
+      cp1->ni = x.x;
+      cp2->ni = x.y;
+      changed = changed || (d.x != 0.0f) || (d.y != 0.0f);
+    }
+  }
+  A.v = vA;
+  A.w = wA;
+  B.v = vB;
+  B.w = wB;
+  storeVel(e, vc.bA, A);
+  storeVel(e, vc.bB, B);
+  return changed;
+}
+
+// b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints for one contact.
+// In a TOI island every contact is (static A, the TOI dynamic body B), so the TOI mass rule
+// ("only the two TOI bodies have mass") reduces to the normal masses.
+HK_HD float solvePositionConstraint(const Scene& S, Env& e, int pid, const Manifold& m, int count, bool toi) {
+  float minSeparation = 0.0f;
+  int fA = S.pairFA[pid], fB = S.pairFB[pid];
+  int bA = fixtureBody(fA), bB = fixtureBody(fB);
+  BodyRef A = bodyRef(S, e, fA), B = bodyRef(S, e, fB);
+  float mA = bA >= 0 ? S.invMass[bA] : 0.0f, iA = bA >= 0 ? S.invI[bA] : 0.0f;
+  float mB = bB >= 0 ? S.invMass[bB] : 0.0f, iB = bB >= 0 ? S.invI[bB] : 0.0f;
+  float radiusA = fixtureRadius(S, fA), radiusB = fixtureRadius(S, fB);
+  V2 cA = A.c, cB = B.c;
+  float aA = A.a, aB = B.a;
+  for (int j = 0; j < count; ++j) {
+    Xf xfA, xfB;
+    xfA.q = rotOf(aA);
+    xfB.q = rotOf(aB);
+    xfA.p = cA - mul(xfA.q, A.lc);
+    xfB.p = cB - mul(xfB.q, B.lc);
+    V2 normal, point;
+    float separation;
+    if (m.type == MANIFOLD_FACE_A) {
+      normal = mul(xfA.q, m.localNormal);
+      V2 planePoint = mul(xfA, m.localPoint);
+      V2 clipPoint = mul(xfB, m.lp[j]);
+      separation = dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+      point = clipPoint;
+    } else {
+      normal = mul(xfB.q, m.localNormal);
+      V2 planePoint = mul(xfB, m.localPoint);
+      V2 clipPoint = mul(xfA, m.lp[j]);
+      separation = dot(clipPoint - planePoint, normal) - radiusA - radiusB;
+      point = clipPoint;
+      normal = -normal;
+    }
+    V2 rA = point - cA;
+    V2 rB = point - cB;
+    minSeparation = fmin2(minSeparation, separation);
+    float C = fclamp((toi ? HK_TOI_BAUMGARTE : HK_BAUMGARTE) * (separation + HK_LINEAR_SLOP), -HK_MAX_LINEAR_CORRECTION, 0.0f);
+    float rnA = cross(rA, normal);
+    float rnB = cross(rB, normal);
+    float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+    float impulse = K > 0.0f ? -C / K : 0.0f;
+    V2 P = impulse * normal;
+    cA -= mA * P;
+    aA -= iA * cross(rA, P);
+    cB += mB * P;
+    aB += iB * cross(rB, P);
+  }
+  if (bA >= 0) {
+    e.b[bA].c = cA;
+    e.b[bA].a = aA;
+  }
+  if (bB >= 0) {
+    e.b[bB].c = cB;
+    e.b[bB].a = aB;
+  }
+  return minSeparation;
+}
+
+HK_HD void integratePosition(Body& b, float h) {
+  V2 translation = h * b.v;
+  if (dot(translation, translation) > HK_MAX_TRANSLATION * HK_MAX_TRANSLATION) {
+    float ratio = HK_MAX_TRANSLATION / length(translation);
+    b.v *= ratio;
+  }
+  float rotation = h * b.w;
+  if (rotation * rotation > HK_MAX_ROTATION * HK_MAX_ROTATION) {
+    float ratio = HK_MAX_ROTATION / fabs2(rotation);
+    b.w *= ratio;
+  }
+  b.c += h * b.v;
+  b.a += h * b.w;
+}
+
+// b2World::Solve: islands by DFS from (puck, racket2, racket1), each solved with b2Island::Solve
+HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h, int velIters, int posIters) {
+  (void)cfg;
+  e.b[0].island = e.b[1].island = e.b[2].island = false;
+  uint32_t inIsland = 0;  // contacts
+  for (int seed = 2; seed >= 0; --seed) {
+    if (e.b[seed].island) continue;
+    if (!e.b[seed].awake) continue;
+    int ic[MAX_MANIFOLDS];
+    int nic = 0;
+    uint32_t bm = 0;
+    int stack[3];
+    int sp = 0;
+    stack[sp++] = seed;
+    e.b[seed].island = true;
+    while (sp > 0) {
+      int bi = stack[--sp];
+      bm |= 1u << bi;
+      setAwake(e.b[bi], true);
+      uint32_t mine = bi == 0 ? HK_PAIRS_R1 : (bi == 1 ? HK_PAIRS_R2 : HK_PAIRS_PUCK);
+      for (int i = 0; i < e.ncontacts; ++i) {
+        int pid = clistGet(e.clist, i);
+        uint32_t bit = 1u << pid;
+        if (!(mine & bit)) continue;
+        if (inIsland & bit) continue;
+        if (!(e.enabled & bit) || !(e.touch & bit)) continue;
+        if (HK_PAIRS_SENSOR & bit) continue;
+        if (nic < MAX_MANIFOLDS) ic[nic++] = pid; else e.nOverflow++;
+        inIsland |= bit;
+        int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
+        int other = (bA == bi) ? bB : bA;
+        if (other < 0) continue;  // statics never propagate the island
+        if (e.b[other].island) continue;
+        stack[sp++] = other;
+        e.b[other].island = true;
+      }
+    }
+    // ---- b2Island::Solve ----
+    for (int bi = 0; bi < 3; ++bi) {
+      if (!((bm >> bi) & 1u)) continue;
+      Body& b = e.b[bi];
+      b.c0 = b.c;
+      b.a0 = b.a;
+      b.v += h * (1.0f * mk(0.0f, 0.0f) + S.invMass[bi] * b.f);
+      b.w += h * S.invI[bi] * b.tq;
+      b.v *= fclamp(1.0f - h * b.ldamp, 0.0f, 1.0f);
+      b.w *= fclamp(1.0f - h * b.adamp, 0.0f, 1.0f);
+    }
+    VC vcs[MAX_MANIFOLDS];
+    int nvc = 0;
+    for (int k = 0; k < nic; ++k) {
+      int pid = ic[k];
+      int slot = findSlot(e, pid);
+      if (slot < 0) {
+        // touching contact whose Collide update was skipped (both bodies were asleep): geometry from the
+        // current poses, ids/impulses from the cache
+        if (e.nmf >= MAX_MANIFOLDS) {
+          e.nOverflow++;
+          continue;
+        }
+        slot = e.nmf++;
+        e.mfPid[slot] = pid;
+        evaluateManifold(S, e, pid, &e.mf[slot]);
+        int oldCount = getCount(e, pid);
+        for (int i = 0; i < e.mf[slot].count; ++i) {
+          e.mf[slot].ni[i] = 0.0f;
+          e.mf[slot].ti[i] = 0.0f;
+          for (int j = 0; j < oldCount; ++j)
+            if (cache.at(pid, j) == e.mf[slot].key[i]) {
+              e.mf[slot].ni[i] = u2f(cache.at(pid, 2 + 2 * j));
+              e.mf[slot].ti[i] = u2f(cache.at(pid, 3 + 2 * j));
+              break;
+            }
+        }
+      }
+      if (e.mf[slot].count == 0) continue;
+      ic[nvc] = pid;
+      initConstraint(S, e, pid, slot, true, &vcs[nvc]);
+      ++nvc;
+    }
+    for (int k = 0; k < nvc; ++k) warmStartConstraint(e, vcs[k]);
+    if (nvc > 0) {
+      for (int it = 0; it < velIters; ++it) {
+        bool changed = false;
+        for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
+        e.nVelIters++;
+        if (!changed) break;  // fixed point: all remaining sweeps are bit-identical no-ops
+      }
+    }
+    // StoreImpulses
+    for (int k = 0; k < nvc; ++k) {
+      Manifold& m = e.mf[vcs[k].slot];
+      for (int j = 0; j < vcs[k].count; ++j) {
+        m.ni[j] = vcs[k].pt[j].ni;
+        m.ti[j] = vcs[k].pt[j].ti;
+        cache.at(ic[k], 2 + 2 * j) = f2u(m.ni[j]);
+        cache.at(ic[k], 3 + 2 * j) = f2u(m.ti[j]);
+      }
+    }
+    for (int bi = 0; bi < 3; ++bi)
+      if ((bm >> bi) & 1u) integratePosition(e.b[bi], h);
+    bool positionSolved = false;
+    for (int it = 0; it < posIters; ++it) {
+      float minSeparation = 0.0f;
+      for (int k = 0; k < nvc; ++k) {
+        const Manifold& m = e.mf[vcs[k].slot];
+        minSeparation = fmin2(minSeparation, solvePositionConstraint(S, e, ic[k], m, m.count, false));
+      }
+      if (minSeparation >= -3.0f * HK_LINEAR_SLOP) {
+        positionSolved = true;
+        break;
+      }
+    }
+    for (int bi = 0; bi < 3; ++bi)
+      if ((bm >> bi) & 1u) syncTransform(S, e.b[bi], bi);
+    {
+      float minSleepTime = HK_MAXFLOAT;
+      const float linTolSqr = HK_LINEAR_SLEEP_TOL * HK_LINEAR_SLEEP_TOL;
+      const float angTolSqr = HK_ANGULAR_SLEEP_TOL * HK_ANGULAR_SLEEP_TOL;
+      for (int bi = 0; bi < 3; ++bi) {
+        if (!((bm >> bi) & 1u)) continue;
+        Body& b = e.b[bi];
+        if (b.w * b.w > angTolSqr || dot(b.v, b.v) > linTolSqr) {
+          b.sleep = 0.0f;
+          minSleepTime = 0.0f;
+        } else {
+          b.sleep += h;
+          minSleepTime = fmin2(minSleepTime, b.sleep);
+        }
+      }
+      if (minSleepTime >= HK_TIME_TO_SLEEP && positionSolved) {
+        for (int bi = 0; bi < 3; ++bi)
+          if ((bm >> bi) & 1u) setAwake(e.b[bi], false);
+      }
+    }
+  }
+  for (int bi = 2; bi >= 0; --bi)
+    if (e.b[bi].island) synchronizeFixtures(S, e, bi);
+  findNewContacts(S, e);
+}
+
+// ---- b2World::SolveTOI: continuous collision of the dynamic bodies against the statics ---------------
+HK_HD Sweep bodySweep(const Scene& S, const Body& b, int bi) {
+  Sweep s;
+  s.lc = mk(S.lcx[bi], S.lcy[bi]);
+  s.c0 = b.c0;
+  s.c = b.c;
+  s.a0 = b.a0;
+  s.a = b.a;
+  s.alpha0 = b.alpha0;
+  return s;
+}
+HK_HD void bodyAdvance(const Scene& S, Body& b, int bi, float alpha) {  // b2Body::Advance
+  Sweep s = bodySweep(S, b, bi);
+  sweepAdvance(s, alpha);
+  b.c0 = s.c0;
+  b.a0 = s.a0;
+  b.alpha0 = s.alpha0;
+  b.c = b.c0;
+  b.a = b.a0;
+  b.q = rotOf(b.a);
+  b.p = b.c - mul(b.q, s.lc);
+}
+
+HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float dt, int velIters) {
+  float salpha[8];  // alpha0 of the 8 static bodies (statics are immovable: only alpha0 advances)
+  for (int i = 0; i < 8; ++i) salpha[i] = 0.0f;
+  e.b[0].island = e.b[1].island = e.b[2].island = false;
+  e.b[0].alpha0 = e.b[1].alpha0 = e.b[2].alpha0 = 0.0f;
+  uint32_t toiFlag = 0;
+  float toi[N_PAIRS];
+  unsigned char toiCount[N_PAIRS];
+  for (int i = 0; i < N_PAIRS; ++i) {
+    toi[i] = 1.0f;
+    toiCount[i] = 0;
+  }
+  for (;;) {
+    int minPid = -1;
+    float minAlpha = 1.0f;
+    for (int i = 0; i < e.ncontacts; ++i) {
+      int pid = clistGet(e.clist, i);
+      uint32_t bit = 1u << pid;
+      if (!(e.enabled & bit)) continue;
+      if (toiCount[pid] > HK_MAX_SUBSTEPS) continue;
+      float alpha = 1.0f;
+      if (toiFlag & bit) {
+        alpha = toi[pid];
+      } else {
+        if (!(HK_PAIRS_TOI & bit)) continue;  // sensors and dynamic-dynamic pairs are skipped
+        int fA = S.pairFA[pid], fB = S.pairFB[pid];
+        int bi = fB - F_R1;
+        Body& B = e.b[bi];
+        if (!B.awake) continue;
+        int sb = staticBodyOf(fA);
+        float alpha0 = salpha[sb];
+        if (salpha[sb] < B.alpha0) {
+          alpha0 = B.alpha0;
+          salpha[sb] = alpha0;
+        } else if (B.alpha0 < salpha[sb]) {
+          alpha0 = salpha[sb];
+          Sweep s = bodySweep(S, B, bi);
+          sweepAdvance(s, alpha0);
+          B.c0 = s.c0;
+          B.a0 = s.a0;
+          B.alpha0 = s.alpha0;
+        }
+        Proxy pA, pB;
+        pA.poly = &S.poly[fA];
+        pA.radius = HK_POLYGON_RADIUS;
+        if (fB == F_PUCK) {
+          pB.poly = nullptr;
+          pB.radius = S.puckRadius;
+        } else {
+          pB.poly = &S.poly[fB];
+          pB.radius = HK_POLYGON_RADIUS;
+        }
+        Sweep sA;
+        sA.lc = mk(0.0f, 0.0f);
+        sA.c0 = sA.c = mk(S.spx[fA], S.spy[fA]);
+        sA.a0 = sA.a = 0.0f;
+        sA.alpha0 = salpha[sb];
+        Sweep sB = bodySweep(S, B, bi);
+        int state;
+        float t;
+        timeOfImpact(&state, &t, pA, sA, pB, sB, 1.0f);
+        float beta = t;
+        if (state == TOI_TOUCHING) alpha = fmin2(alpha0 + (1.0f - alpha0) * beta, 1.0f);
+        else alpha = 1.0f;
+        toi[pid] = alpha;
+        toiFlag |= bit;
+      }
+      if (alpha < minAlpha) {
+        minPid = pid;
+        minAlpha = alpha;
+      }
+    }
+    if (minPid < 0 || 1.0f - 10.0f * HK_EPS < minAlpha) break;
+    e.nToiEvents++;
+
+    const int fA = S.pairFA[minPid], fB = S.pairFB[minPid];
+    const int bi = fB - F_R1;
+    const int sbA = staticBodyOf(fA);
+    Body& B = e.b[bi];
+    const Body backupB = B;
+    const float backupSA = salpha[sbA];
+    salpha[sbA] = minAlpha;
+    bodyAdvance(S, B, bi, minAlpha);
+    updateContact(S, cfg, cache, e, minPid);
+    toiFlag &= ~(1u << minPid);
+    ++toiCount[minPid];
+    if (!(e.enabled & (1u << minPid)) || !(e.touch & (1u << minPid))) {
+      e.enabled &= ~(1u << minPid);
+      // restore sweeps (awake/sleep changes made by Update persist, as in b2World::SolveTOI)
+      salpha[sbA] = backupSA;
+      B.c0 = backupB.c0;
+      B.c = backupB.c;
+      B.a0 = backupB.a0;
+      B.a = backupB.a;
+      B.alpha0 = backupB.alpha0;
+      syncTransform(S, B, bi);
+      continue;
+    }
+    setAwake(B, true);
+    int ic[MAX_MANIFOLDS];
+    int nic = 0;
+    ic[nic++] = minPid;
+    uint32_t inIsland = 1u << minPid;
+    uint32_t staticIsland = 1u << sbA;
+    const uint32_t mine = bi == 0 ? HK_PAIRS_R1 : (bi == 1 ? HK_PAIRS_R2 : HK_PAIRS_PUCK);
+    for (int i = 0; i < e.ncontacts; ++i) {
+      int pid = clistGet(e.clist, i);
+      uint32_t bit = 1u << pid;
+      if (!(mine & bit)) continue;
+      if (nic == MAX_MANIFOLDS) break;
+      if (inIsland & bit) continue;
+      if (!(HK_PAIRS_TOI & bit)) continue;  // other body dynamic, or sensor
+      int so = staticBodyOf(S.pairFA[pid]);
+      float backup = salpha[so];
+      if (!((staticIsland >> so) & 1u)) salpha[so] = minAlpha;
+      updateContact(S, cfg, cache, e, pid);
+      if (!(e.enabled & bit) || !(e.touch & bit)) {
+        salpha[so] = backup;
+        continue;
+      }
+      inIsland |= bit;
+      ic[nic++] = pid;
+      staticIsland |= 1u << so;
+    }
+    const float subDt = (1.0f - minAlpha) * dt;
+    // ---- b2Island::SolveTOI ----
+    for (int it = 0; it < 20; ++it) {
+      float minSeparation = 0.0f;
+      for (int k = 0; k < nic; ++k) {
+        int slot = findSlot(e, ic[k]);
+        if (slot < 0) continue;
+        const Manifold& m = e.mf[slot];
+        minSeparation = fmin2(minSeparation, solvePositionConstraint(S, e, ic[k], m, m.count, true));
+      }
+      if (minSeparation >= -1.5f * HK_LINEAR_SLOP) break;
+    }
+    B.c0 = B.c;
+    B.a0 = B.a;
+    VC vcs[MAX_MANIFOLDS];
+    int nvc = 0;
+    for (int k = 0; k < nic; ++k) {
+      int slot = findSlot(e, ic[k]);
+      if (slot < 0 || e.mf[slot].count == 0) continue;
+      initConstraint(S, e, ic[k], slot, false, &vcs[nvc]);
+      ++nvc;
+    }
+    for (int it = 0; it < velIters; ++it) {
+      bool changed = false;
+      for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
+      e.nVelIters++;
+      if (!changed) break;
+    }
+    integratePosition(B, subDt);
+    syncTransform(S, B, bi);
+    B.island = false;
+    synchronizeFixtures(S, e, bi);
+    toiFlag &= ~mine;
+    findNewContacts(S, e);
+  }
+}
+
+// b2World::Step(dt, velocityIterations, positionIterations)
+HK_HD void worldStep(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float dt, int velIters, int posIters) {
+  e.enabled = 0xFFFFFFFFu;
+  e.nmf = 0;
+  if (e.moved & 8u) {
+    e.moved &= ~8u;
+    findNewContacts(S, e);
+  }
+  collide(S, cfg, cache, e);
+  solveIslands(S, cfg, cache, e, dt, velIters, posIters);
+  if (e.exist & HK_PAIRS_TOI) solveTOI(S, cfg, cache, e, dt, velIters);
+  for (int bi = 0; bi < 3; ++bi) {  // ClearForces
+    e.b[bi].f = mk(0.0f, 0.0f);
+    e.b[bi].tq = 0.0f;
+  }
+}
+
+}  // namespace hk

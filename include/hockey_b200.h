@@ -81,6 +81,7 @@ enum {
   HK_S_EPISODE = 48,  /* u32 episodes started (RNG counter for reset draws) */
   HK_S_TICK = 49,     /* u32 ticks executed since creation (RNG counter for per-tick draws) */
   HK_S_RET = 50,      /* 2 f64: running episode return of player 1 and player 2 (statistics only) */
+  HK_S_PUCK_C0 = 54,  /* 2 f32: b2Sweep::c0 of the puck (only read if the puck is woken mid-step while asleep) */
   HK_S_CONTACT = 64,  /* HK_N_PAIRS records of HK_CONTACT_WORDS words */
   HK_N_PAIRS = 27,
   HK_CONTACT_WORDS = 8,

@@ -557,6 +557,8 @@ static void packState(Env* e, uint32_t* r) {
   r[HK_S_EPISODE] = e->episode;
   r[HK_S_TICK] = e->tick;
   std::memcpy(r + HK_S_RET, e->ret, 16);
+  r[HK_S_PUCK_C0] = f2u(pk.sweep.c0.x);
+  r[HK_S_PUCK_C0 + 1] = f2u(pk.sweep.c0.y);
   for (size_t i = 0; i < e->world.contacts.size(); ++i) {
     Contact* c = e->world.contacts[i];
     int pid = pairId(c->fA, c->fB);
@@ -588,7 +590,8 @@ static void unpackState(Env* e, const uint32_t* r) {
   }
   Body& pk = e->body(B_PUCK);
   const uint32_t* p = r + HK_S_PUCK;
-  pk.sweep.c = pk.sweep.c0 = mk(u2f(p[0]), u2f(p[1]));
+  pk.sweep.c = mk(u2f(p[0]), u2f(p[1]));
+  pk.sweep.c0 = mk(u2f(r[HK_S_PUCK_C0]), u2f(r[HK_S_PUCK_C0 + 1]));
   pk.xf.p = pk.sweep.c;
   pk.sweep.a = pk.sweep.a0 = u2f(p[2]);
   pk.xf.q.set(pk.sweep.a);

@@ -1,0 +1,88 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Compiles the product's device headers (hockey_env_b200/csrc/*.cuh) for the HOST so that the
+// non-GPU test tier can diff the kernel's per-env arithmetic against the CPU oracle bit-for-bit
+// (there is no GPU in the build container).  It is not reachable from the hockey_env_b200 package
+// and is never a fallback: the package fails loudly without the CUDA library.
+#include <cstring>
+#include <vector>
+#include "../../include/hockey_b200.h"
+#include "../../hockey_env_b200/csrc/hk_tick.cuh"
+
+using namespace hk;
+
+struct HostBatch {
+  Scene S;
+  Config cfg;
+  int64_t n, env_id_offset;
+  std::vector<Env> envs;
+  std::vector<uint32_t> cache;  // [27*6][n]
+  double stats[HK_STATS_DIM];
+  Cache cacheOf(int64_t i) { Cache c; c.base = cache.data() + i; c.stride = (size_t)n; return c; }
+};
+
+static void addStats(double* s, const TickStats& t) {
+  s[0] += t.episodes; s[1] += t.wins; s[2] += t.losses; s[3] += t.draws; s[4] += t.steps;
+  s[5] += t.ret1; s[6] += t.ret2; s[7] += t.ret1sq; s[8] += t.len; s[9] += t.touch1; s[10] += t.touch2;
+  s[11] += t.velIters; s[12] += t.toi; s[13] += t.overflow;
+}
+
+extern "C" {
+void* hs_create(int64_t n, int mode, int keep_mode, uint64_t seed, int64_t env_id_offset) {
+  HostBatch* b = new HostBatch();
+  scene_build::build(&b->S);
+  b->cfg.mode = mode; b->cfg.keep_mode = keep_mode; b->cfg.max_timesteps = mode == 0 ? 250 : 80; b->cfg.seed = seed;
+  b->n = n; b->env_id_offset = env_id_offset;
+  b->envs.resize(n);
+  b->cache.assign((size_t)n * 27 * 6, 0);
+  std::memset(b->stats, 0, sizeof(b->stats));
+  for (int64_t i = 0; i < n; ++i) { std::memset(&b->envs[i], 0, sizeof(Env)); envCreate(b->S, b->cfg, b->envs[i], (uint64_t)(env_id_offset + i)); }
+  return b;
+}
+void hs_destroy(void* h) { delete (HostBatch*)h; }
+void hs_reset(void* h, const uint8_t* mask, const int8_t* one_starting, float* obs) {
+  HostBatch* b = (HostBatch*)h;
+  for (int64_t i = 0; i < b->n; ++i) {
+    if (mask && !mask[i]) continue;
+    envReset(b->S, b->cfg, b->envs[i], (uint64_t)(b->env_id_offset + i), one_starting ? (int)one_starting[i] : -1);
+    if (obs) getObs(b->envs[i], obs + 18 * i);
+  }
+}
+void hs_step(void* h, const float* action, int stride, int pol1, int pol2, int flags, float* obs, float* obs2, float* reward,
+             float* reward2, uint8_t* done, float* info, float* info2, float* final_obs) {
+  HostBatch* b = (HostBatch*)h;
+  StepIO io; io.action = action; io.stride = stride; io.pol1 = pol1; io.pol2 = pol2; io.flags = flags; io.obs = obs; io.obs2 = obs2;
+  io.reward = reward; io.reward2 = reward2; io.done = done; io.info = info; io.info2 = info2; io.final_obs = final_obs;
+  for (int64_t i = 0; i < b->n; ++i) {
+    // round-trip through the HBM group layout exactly as the kernel does
+    F4 g[CORE_GROUPS];
+    envToGroups(b->envs[i], g);
+    Env e;
+    groupsToEnv(g, e);
+    TickStats st; tickStatsZero(st);
+    envTick(b->S, b->cfg, b->cacheOf(i), e, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st);
+    b->envs[i] = e;
+    addStats(b->stats, st);
+  }
+}
+void hs_get_obs(void* h, float* obs, float* obs2) {
+  HostBatch* b = (HostBatch*)h;
+  for (int64_t i = 0; i < b->n; ++i) { if (obs) getObs(b->envs[i], obs + 18 * i); if (obs2) getObs2(b->envs[i], obs2 + 18 * i); }
+}
+void hs_get_state(void* h, uint32_t* rec) {
+  HostBatch* b = (HostBatch*)h;
+  for (int64_t i = 0; i < b->n; ++i) packRecord(b->envs[i], b->cacheOf(i), rec + (size_t)HK_STATE_WORDS * i);
+}
+void hs_set_state(void* h, const uint32_t* rec) {
+  HostBatch* b = (HostBatch*)h;
+  for (int64_t i = 0; i < b->n; ++i) unpackRecord(rec + (size_t)HK_STATE_WORDS * i, b->envs[i], b->cacheOf(i));
+}
+void hs_set_obs_state(void* h, const float* obs18) {
+  HostBatch* b = (HostBatch*)h;
+  for (int64_t i = 0; i < b->n; ++i) setObsState(b->S, b->envs[i], obs18 + 18 * i, b->cfg.keep_mode);
+}
+void hs_get_stats(void* h, double* out) { std::memcpy(out, ((HostBatch*)h)->stats, sizeof(double) * HK_STATS_DIM); }
+void hs_clear_stats(void* h) { std::memset(((HostBatch*)h)->stats, 0, sizeof(double) * HK_STATS_DIM); }
+void hs_scene(void* h, void* out, int64_t nbytes) { std::memcpy(out, &((HostBatch*)h)->S, (size_t)nbytes < sizeof(Scene) ? (size_t)nbytes : sizeof(Scene)); }
+int64_t hs_scene_size() { return (int64_t)sizeof(Scene); }
+}

@@ -1,0 +1,15 @@
+"""hockey_env_b200 -- B200-native batched HockeyEnv (drop-in for hockey.hockey_env of julilili42/hockey-env).
+
+The hot path (HockeyEnv.step/reset incl. the Box2D world step, contact sensing, rewards, observations,
+BasicOpponent and auto-reset) runs in hand-written sm_100a CUDA kernels behind the C ABI declared in
+include/hockey_b200.h; this package is the thin host-side mirror of the reference's Python surface.
+"""
+from ._lib import HockeyLibraryError, load as load_library  # noqa: F401
+from .env import (  # noqa: F401
+    BasicOpponent, HockeyEnv, HockeyEnv_BasicOpponent, HockeyVecEnv, Mode, PolicyOpponent,
+    FPS, SCALE, VIEWPORT_W, VIEWPORT_H, W, H, CENTER_X, CENTER_Y, ZONE, MAX_ANGLE, MAX_TIME_KEEP_PUCK, GOAL_SIZE,
+    RACKETPOLY, RACKETFACTOR, FORCEMULTIPLIER, SHOOTFORCEMULTIPLIER, TORQUEMULTIPLIER, MAX_PUCK_SPEED,
+)
+
+__all__ = ["HockeyVecEnv", "HockeyEnv", "HockeyEnv_BasicOpponent", "BasicOpponent", "PolicyOpponent", "Mode",
+           "HockeyLibraryError", "load_library"]

@@ -1,0 +1,460 @@
+// hk_lib.cu -- CUDA kernels and the C ABI (include/hockey_b200.h) of the batched HockeyEnv.
+//
+// One env per thread.  Each kernel stages the constant Scene into shared memory (polygon tables are
+// indexed with per-lane indices in the narrow phase; shared memory serves divergent addresses far
+// better than the constant cache), loads the env's 16 float4 groups with coalesced 128-bit
+// accesses, runs hk::envTick and stores the groups back.  No tensor cores: the path is scalar
+// fp32/fp64 integer-and-branch work (see DESIGN.md for the roofline discussion).
+//
+// Built for sm_100a only, with -fmad=false (see hk_math.cuh).  There is no CPU fallback in this
+// library: without a CUDA device hk_create fails with HK_E_NODEVICE.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/hockey_b200.h"
+#include "hk_tick.cuh"
+
+using namespace hk;
+
+namespace {
+
+__constant__ Scene c_scene;
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define HK_CUDA(call)                                                                           \
+  do {                                                                                          \
+    cudaError_t _e = (call);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(HK_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ void stageScene(Scene* dst) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_scene);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  for (int k = threadIdx.x; k < (int)(sizeof(Scene) / 4); k += blockDim.x) d[k] = src[k];
+  __syncthreads();
+}
+
+__device__ __forceinline__ void loadEnv(const float4* __restrict__ core, int64_t n, int64_t i, Env& e) {
+  F4 g[CORE_GROUPS];
+#pragma unroll
+  for (int k = 0; k < CORE_GROUPS; ++k) {
+    float4 v = core[(int64_t)k * n + i];
+    g[k] = F4{v.x, v.y, v.z, v.w};
+  }
+  groupsToEnv(g, e);
+}
+__device__ __forceinline__ void storeEnv(float4* __restrict__ core, int64_t n, int64_t i, const Env& e) {
+  F4 g[CORE_GROUPS];
+  envToGroups(e, g);
+#pragma unroll
+  for (int k = 0; k < CORE_GROUPS; ++k) core[(int64_t)k * n + i] = make_float4(g[k].x, g[k].y, g[k].z, g[k].w);
+}
+
+__device__ __forceinline__ void flushInt(double* gstats, int slot, int v, int lane) {
+  int s = __reduce_add_sync(0xffffffffu, v);
+  if (lane == 0 && s != 0) atomicAdd(&gstats[slot], (double)s);
+}
+__device__ __forceinline__ double warpSumD(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+// per-env contact reductions -> warp shuffles/redux, one atomic per warp and statistic
+__device__ __forceinline__ void flushStats(double* gstats, const TickStats& st) {
+  const int lane = threadIdx.x & 31;
+  flushInt(gstats, 4, st.steps, lane);
+  flushInt(gstats, 11, st.velIters, lane);
+  flushInt(gstats, 9, st.touch1, lane);
+  flushInt(gstats, 10, st.touch2, lane);
+  flushInt(gstats, 12, st.toi, lane);
+  flushInt(gstats, 13, st.overflow, lane);
+  if (__any_sync(0xffffffffu, st.episodes != 0)) {
+    flushInt(gstats, 0, st.episodes, lane);
+    flushInt(gstats, 1, st.wins, lane);
+    flushInt(gstats, 2, st.losses, lane);
+    flushInt(gstats, 3, st.draws, lane);
+    flushInt(gstats, 8, st.len, lane);
+    double a = warpSumD(st.ret1), b = warpSumD(st.ret2), c = warpSumD(st.ret1sq);
+    if (lane == 0) {
+      atomicAdd(&gstats[5], a);
+      atomicAdd(&gstats[6], b);
+      atomicAdd(&gstats[7], c);
+    }
+  }
+}
+
+struct KParams {
+  float4* core;
+  uint32_t* cache;
+  double* stats;
+  int64_t n;
+  int64_t env_id_offset;
+  Config cfg;
+};
+
+__global__ void __launch_bounds__(kBlock) k_create(KParams P) {
+  __shared__ Scene S;
+  stageScene(&S);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  Env e;
+  envCreate(S, P.cfg, e, (uint64_t)(P.env_id_offset + i));
+  storeEnv(P.core, P.n, i, e);
+}
+
+__global__ void __launch_bounds__(kBlock) k_reset(KParams P, const uint8_t* mask, const int8_t* one_starting, float* obs) {
+  __shared__ Scene S;
+  stageScene(&S);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  if (mask && !mask[i]) return;
+  Env e;
+  loadEnv(P.core, P.n, i, e);
+  envReset(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), one_starting ? (int)one_starting[i] : -1);
+  storeEnv(P.core, P.n, i, e);
+  if (obs) {
+    float o[18];
+    getObs(e, o);
+    writeRow18(obs + 18 * i, o);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_step(KParams P, StepIO io) {
+  __shared__ Scene S;
+  stageScene(&S);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  TickStats st;
+  tickStatsZero(st);
+  if (i < P.n) {
+    Env e;
+    loadEnv(P.core, P.n, i, e);
+    Cache cache;
+    cache.base = P.cache + i;
+    cache.stride = (size_t)P.n;
+    envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st);
+    storeEnv(P.core, P.n, i, e);
+  }
+  flushStats(P.stats, st);
+}
+
+// K fused ticks: body state stays in registers/local memory across ticks, HBM state traffic is paid once
+__global__ void __launch_bounds__(kBlock) k_rollout(KParams P, StepIO io, int k_steps) {
+  __shared__ Scene S;
+  stageScene(&S);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  TickStats st;
+  tickStatsZero(st);
+  if (i < P.n) {
+    Env e;
+    loadEnv(P.core, P.n, i, e);
+    Cache cache;
+    cache.base = P.cache + i;
+    cache.stride = (size_t)P.n;
+    for (int s = 0; s < k_steps; ++s)
+      envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, s == k_steps - 1, st);
+    storeEnv(P.core, P.n, i, e);
+  }
+  flushStats(P.stats, st);
+}
+
+__global__ void __launch_bounds__(kBlock) k_get_obs(KParams P, float* obs, float* obs2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  Env e;
+  loadEnv(P.core, P.n, i, e);
+  float o[18];
+  if (obs) {
+    getObs(e, o);
+    writeRow18(obs + 18 * i, o);
+  }
+  if (obs2) {
+    getObs2(e, o);
+    writeRow18(obs2 + 18 * i, o);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_get_info(KParams P, float* info, float* info2) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  Env e;
+  loadEnv(P.core, P.n, i, e);
+  double v[4];
+  if (info) {
+    getInfo(P.cfg, e, false, v);
+    for (int k = 0; k < 4; ++k) info[4 * i + k] = (float)v[k];
+  }
+  if (info2) {
+    getInfo(P.cfg, e, true, v);
+    for (int k = 0; k < 4; ++k) info2[4 * i + k] = (float)v[k];
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_get_state(KParams P, uint32_t* rec) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  Env e;
+  loadEnv(P.core, P.n, i, e);
+  Cache cache;
+  cache.base = P.cache + i;
+  cache.stride = (size_t)P.n;
+  packRecord(e, cache, rec + (size_t)HK_STATE_WORDS * i);
+}
+
+__global__ void __launch_bounds__(kBlock) k_set_state(KParams P, const uint32_t* rec) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  Env e;
+  Cache cache;
+  cache.base = P.cache + i;
+  cache.stride = (size_t)P.n;
+  unpackRecord(rec + (size_t)HK_STATE_WORDS * i, e, cache);
+  storeEnv(P.core, P.n, i, e);
+}
+
+__global__ void __launch_bounds__(kBlock) k_set_obs_state(KParams P, const float* obs18) {
+  __shared__ Scene S;
+  stageScene(&S);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  Env e;
+  loadEnv(P.core, P.n, i, e);
+  setObsState(S, e, obs18 + 18 * i, P.cfg.keep_mode);
+  storeEnv(P.core, P.n, i, e);
+}
+
+}  // namespace
+
+struct hk_env {
+  int64_t n;
+  int device;
+  int64_t env_id_offset;
+  Config cfg;
+  float4* core;
+  uint32_t* cache;
+  double* stats;
+  KParams params() const {
+    KParams P;
+    P.core = core;
+    P.cache = cache;
+    P.stats = stats;
+    P.n = n;
+    P.env_id_offset = env_id_offset;
+    P.cfg = cfg;
+    return P;
+  }
+  unsigned grid() const { return (unsigned)((n + kBlock - 1) / kBlock); }
+};
+
+static bool validPolicy(int p) { return p >= HK_POLICY_EXTERNAL && p <= HK_POLICY_ZERO; }
+
+extern "C" {
+
+const char* hk_last_error(void) { return g_err.c_str(); }
+const char* hk_version(void) { return "hockey_b200 0.1 (sm_100a, fmad=false)"; }
+
+int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device, uint64_t seed, int64_t env_id_offset) {
+  if (!out) return fail(HK_E_INVALID, "hk_create: out is NULL");
+  *out = nullptr;
+  if (n_envs <= 0) return fail(HK_E_INVALID, "hk_create: n_envs must be positive");
+  if (mode < HK_MODE_NORMAL || mode > HK_MODE_TRAIN_DEFENSE)
+    return fail(HK_E_INVALID, std::to_string(mode) + " is not a valid value for Mode");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(HK_E_NODEVICE, "hk_create: no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= count) return fail(HK_E_INVALID, "hk_create: bad device index");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HK_E_CUDA, "hk_create: cannot select device");
+  hk_env* h = new hk_env();
+  h->n = n_envs;
+  h->device = device;
+  h->env_id_offset = env_id_offset;
+  h->cfg.mode = mode;
+  h->cfg.keep_mode = keep_mode ? 1 : 0;
+  h->cfg.max_timesteps = mode == HK_MODE_NORMAL ? 250 : 80;  // hockey_env.py:357-364
+  h->cfg.seed = seed;
+  h->core = nullptr;
+  h->cache = nullptr;
+  h->stats = nullptr;
+  Scene S;
+  std::memset(&S, 0, sizeof(S));
+  scene_build::build(&S);
+  cudaError_t err = cudaMemcpyToSymbol(c_scene, &S, sizeof(Scene));
+  if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);
+  if (err == cudaSuccess) err = cudaMalloc(&h->cache, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
+  if (err == cudaSuccess) err = cudaMalloc(&h->stats, sizeof(double) * HK_STATS_DIM);
+  if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
+  if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
+  if (err == cudaSuccess) {
+    k_create<<<h->grid(), kBlock>>>(h->params());
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) {
+    std::string msg = std::string("hk_create: ") + cudaGetErrorString(err);
+    cudaFree(h->core);
+    cudaFree(h->cache);
+    cudaFree(h->stats);
+    delete h;
+    return fail(HK_E_CUDA, msg);
+  }
+  *out = h;
+  return HK_OK;
+}
+
+int hk_destroy(hk_env* h) {
+  if (!h) return HK_OK;
+  DeviceGuard guard(h->device);
+  cudaFree(h->core);
+  cudaFree(h->cache);
+  cudaFree(h->stats);
+  delete h;
+  return HK_OK;
+}
+
+int64_t hk_num_envs(const hk_env* h) { return h ? h->n : 0; }
+
+int hk_reset(hk_env* h, const uint8_t* mask_dev, const int8_t* one_starting_dev, float* obs_dev, void* stream) {
+  if (!h) return fail(HK_E_INVALID, "hk_reset: NULL handle");
+  DeviceGuard guard(h->device);
+  k_reset<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), mask_dev, one_starting_dev, obs_dev);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy, int p2_policy, int flags, float* obs_dev,
+            float* obs2_dev, float* reward_dev, float* reward2_dev, uint8_t* done_dev, float* info_dev, float* info2_dev,
+            float* final_obs_dev, void* stream) {
+  if (!h) return fail(HK_E_INVALID, "hk_step: NULL handle");
+  if (!validPolicy(p1_policy) || !validPolicy(p2_policy)) return fail(HK_E_INVALID, "hk_step: invalid policy id");
+  if (!obs_dev) return fail(HK_E_INVALID, "hk_step: obs_dev is required");
+  if ((p1_policy == HK_POLICY_EXTERNAL || p2_policy == HK_POLICY_EXTERNAL) && !action_dev)
+    return fail(HK_E_INVALID, "hk_step: action_dev is NULL but a policy is EXTERNAL");
+  if (p1_policy == HK_POLICY_EXTERNAL && action_stride < 4) return fail(HK_E_INVALID, "hk_step: action_stride < 4");
+  if (p2_policy == HK_POLICY_EXTERNAL && action_stride < 8)
+    return fail(HK_E_INVALID, "hk_step: player 2 EXTERNAL needs action_stride >= 8");
+  DeviceGuard guard(h->device);
+  StepIO io;
+  io.action = action_dev;
+  io.stride = action_stride;
+  io.pol1 = p1_policy;
+  io.pol2 = p2_policy;
+  io.flags = flags;
+  io.obs = obs_dev;
+  io.obs2 = obs2_dev;
+  io.reward = reward_dev;
+  io.reward2 = reward2_dev;
+  io.done = done_dev;
+  io.info = info_dev;
+  io.info2 = info2_dev;
+  io.final_obs = final_obs_dev;
+  k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_rollout(hk_env* h, int k_steps, int p1_policy, int p2_policy, float* obs_dev, void* stream) {
+  if (!h) return fail(HK_E_INVALID, "hk_rollout: NULL handle");
+  if (k_steps <= 0) return fail(HK_E_INVALID, "hk_rollout: k_steps must be positive");
+  if (!validPolicy(p1_policy) || !validPolicy(p2_policy) || p1_policy == HK_POLICY_EXTERNAL || p2_policy == HK_POLICY_EXTERNAL)
+    return fail(HK_E_INVALID, "hk_rollout: policies must be in-kernel (not EXTERNAL)");
+  DeviceGuard guard(h->device);
+  StepIO io;
+  std::memset(&io, 0, sizeof(io));
+  io.pol1 = p1_policy;
+  io.pol2 = p2_policy;
+  io.flags = HK_STEP_AUTORESET;
+  io.obs = obs_dev;
+  k_rollout<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io, k_steps);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_get_obs(hk_env* h, float* obs_dev, float* obs2_dev, void* stream) {
+  if (!h) return fail(HK_E_INVALID, "hk_get_obs: NULL handle");
+  DeviceGuard guard(h->device);
+  k_get_obs<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), obs_dev, obs2_dev);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_get_info(hk_env* h, float* info_dev, float* info2_dev, void* stream) {
+  if (!h) return fail(HK_E_INVALID, "hk_get_info: NULL handle");
+  DeviceGuard guard(h->device);
+  k_get_info<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), info_dev, info2_dev);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_get_state(hk_env* h, uint32_t* state_dev, void* stream) {
+  if (!h || !state_dev) return fail(HK_E_INVALID, "hk_get_state: NULL argument");
+  DeviceGuard guard(h->device);
+  k_get_state<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), state_dev);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_set_state(hk_env* h, const uint32_t* state_dev, void* stream) {
+  if (!h || !state_dev) return fail(HK_E_INVALID, "hk_set_state: NULL argument");
+  DeviceGuard guard(h->device);
+  k_set_state<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), state_dev);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_set_obs_state(hk_env* h, const float* obs18_dev, void* stream) {
+  if (!h || !obs18_dev) return fail(HK_E_INVALID, "hk_set_obs_state: NULL argument");
+  DeviceGuard guard(h->device);
+  k_set_obs_state<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), obs18_dev);
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_get_stats(hk_env* h, double* out_host, void* stream) {
+  if (!h || !out_host) return fail(HK_E_INVALID, "hk_get_stats: NULL argument");
+  DeviceGuard guard(h->device);
+  HK_CUDA(cudaMemcpyAsync(out_host, h->stats, sizeof(double) * HK_STATS_DIM, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  HK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return HK_OK;
+}
+
+int hk_clear_stats(hk_env* h, void* stream) {
+  if (!h) return fail(HK_E_INVALID, "hk_clear_stats: NULL handle");
+  DeviceGuard guard(h->device);
+  HK_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(double) * HK_STATS_DIM, (cudaStream_t)stream));
+  return HK_OK;
+}
+
+int hk_copy_stats(hk_env* h, double* dst_dev, void* stream) {
+  if (!h || !dst_dev) return fail(HK_E_INVALID, "hk_copy_stats: NULL argument");
+  DeviceGuard guard(h->device);
+  HK_CUDA(cudaMemcpyAsync(dst_dev, h->stats, sizeof(double) * HK_STATS_DIM, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HK_OK;
+}
+
+int hk_stats_device_ptr(hk_env* h, double** out_dev) {
+  if (!h || !out_dev) return fail(HK_E_INVALID, "hk_stats_device_ptr: NULL argument");
+  *out_dev = h->stats;
+  return HK_OK;
+}
+
+}  // extern "C"

@@ -72,7 +72,6 @@ HK_HD int fixtureBody(int f) { return f < N_STATIC_FIX ? -1 : f - F_R1; }
 #define HK_PAIRS_SENSOR 0x01800000u  /* 23, 24 */
 #define HK_PAIRS_TOI 0x007EFFFFu     /* static x dynamic, non-sensor: 0-15, 17-22 */
 
-#if !defined(__CUDA_ARCH__)
 // ---- host-side scene construction: restates b2PolygonShape::Set / ComputeMass / b2CircleShape::
 // ComputeMass / b2Body::ResetMassData (Box2D 2.3.0) in float32 for the vertex lists of
 // hockey_env.py:31-32,188-195,209-214,228-232,307-317,327-338,373-375. ---------------------------
@@ -307,6 +306,5 @@ inline void build(Scene* S) {
 }
 
 }  // namespace scene_build
-#endif
 
 }  // namespace hk

@@ -1,0 +1,557 @@
+"""Host-side mirror of the reference's gym-facing surface (hockey/hockey_env.py) over the CUDA library.
+
+`HockeyVecEnv` is the batched, zero-copy API (torch CUDA tensors in/out, one kernel launch per tick).
+`HockeyEnv`, `HockeyEnv_BasicOpponent`, `BasicOpponent`, `PolicyOpponent`, `Mode` keep the reference's
+names, signatures and semantics (single env = batch of 1) so that code written against
+`hockey.hockey_env` runs unchanged.  PyTorch is used only for device memory and streams.
+"""
+import ctypes as C
+import math
+from enum import Enum
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# constants of the reference module (hockey_env.py:17-37)
+FPS = 50
+SCALE = 60.0
+VIEWPORT_W = 600
+VIEWPORT_H = 480
+W = VIEWPORT_W / SCALE
+H = VIEWPORT_H / SCALE
+CENTER_X = W / 2
+CENTER_Y = H / 2
+ZONE = W / 20
+MAX_ANGLE = math.pi / 3
+MAX_TIME_KEEP_PUCK = 15
+GOAL_SIZE = 75
+RACKETPOLY = [(-10, 20), (+5, 20), (+5, -20), (-10, -20), (-18, -10), (-21, 0), (-18, 10)]
+RACKETFACTOR = 1.2
+FORCEMULTIPLIER = 6000
+SHOOTFORCEMULTIPLIER = 60
+TORQUEMULTIPLIER = 400
+MAX_PUCK_SPEED = 25
+
+
+class Mode(Enum):  # hockey_env.py:78-81
+    NORMAL = 0
+    TRAIN_SHOOTING = 1
+    TRAIN_DEFENSE = 2
+
+
+def _as_mode(value):
+    """Accept an Enum member, a name or an int, with the reference's errors (hockey_env.py:758-779)."""
+    if isinstance(value, Mode):
+        return value
+    if isinstance(value, str):
+        try:
+            return Mode[value]
+        except KeyError:
+            raise ValueError(f"{value} is not a valid name for {Mode.__name__}")
+    if isinstance(value, (int, np.integer)) and not isinstance(value, bool):
+        try:
+            return Mode(int(value))
+        except ValueError:
+            raise ValueError(f"{value} is not a valid value for {Mode.__name__}")
+    raise TypeError("Input value must be an Enum, name (str), or value (int)")
+
+
+_POLICY_IDS = {
+    None: _lib.POLICY_EXTERNAL, "external": _lib.POLICY_EXTERNAL,
+    "weak": _lib.POLICY_BASIC_WEAK, "basic_weak": _lib.POLICY_BASIC_WEAK,
+    "strong": _lib.POLICY_BASIC_STRONG, "basic_strong": _lib.POLICY_BASIC_STRONG,
+    "random": _lib.POLICY_RANDOM, "zero": _lib.POLICY_ZERO,
+}
+
+
+def _policy_id(p):
+    if isinstance(p, (int, np.integer)) and not isinstance(p, bool):
+        return int(p)
+    try:
+        return _POLICY_IDS[p]
+    except KeyError:
+        raise ValueError(f"unknown policy {p!r}; use one of {sorted(k for k in _POLICY_IDS if k)}")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class HockeyVecEnv:
+    """N independent HockeyEnvs stepped by one CUDA launch per tick.
+
+    All tensors returned by `reset`/`step` are persistent device buffers owned by this object and are
+    overwritten by the next call (zero-copy; clone() to keep).  Work is enqueued on the current torch
+    CUDA stream; nothing synchronises the host.
+
+    p1 / p2: None (actions come from the caller) or 'weak' / 'strong' (in-kernel BasicOpponent,
+    hockey_env.py:781-833) / 'random' / 'zero'.  With p2 set, `step` takes [N,4] actions like
+    HockeyEnv_BasicOpponent (hockey_env.py:875-886); otherwise [N,8] like HockeyEnv.
+    """
+
+    def __init__(self, num_envs, mode=Mode.NORMAL, keep_mode=True, device="cuda:0", seed=0, env_id_offset=0,
+                 auto_reset=True, p1=None, p2=None, want_agent_two=False):
+        self.L = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.HockeyLibraryError("no CUDA device: hockey_env_b200 has no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("HockeyVecEnv needs a CUDA device")
+        self.num_envs = int(num_envs)
+        self._mode = _as_mode(mode)
+        self.keep_mode = bool(keep_mode)
+        self.auto_reset = bool(auto_reset)
+        self.p1 = _policy_id(p1)
+        self.p2 = _policy_id(p2)
+        self.want_agent_two = bool(want_agent_two)
+        self.max_timesteps = 250 if self._mode == Mode.NORMAL else 80
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        _lib.check(self.L.hk_create(C.byref(h), self.num_envs, self._mode.value, int(self.keep_mode), dev_index,
+                                    int(seed) & 0xFFFFFFFFFFFFFFFF, int(env_id_offset)))
+        self._h = h
+        n, d = self.num_envs, self.device
+        self.obs = torch.empty((n, 18), dtype=torch.float32, device=d)
+        self.reward = torch.empty(n, dtype=torch.float32, device=d)
+        self.done = torch.empty(n, dtype=torch.uint8, device=d)
+        self.truncated = torch.zeros(n, dtype=torch.bool, device=d)  # always False (hockey_env.py:695)
+        self.info = torch.empty((n, 4), dtype=torch.float32, device=d)
+        self.final_obs = torch.empty((n, 18), dtype=torch.float32, device=d) if self.auto_reset else None
+        self.obs2 = self.reward2 = self.info2 = None
+        if self.want_agent_two:
+            self.obs2 = torch.empty((n, 18), dtype=torch.float32, device=d)
+            self.reward2 = torch.empty(n, dtype=torch.float32, device=d)
+            self.info2 = torch.empty((n, 4), dtype=torch.float32, device=d)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_get_obs(self._h, _ptr(self.obs), _ptr(self.obs2), self._stream()))
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.hk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def mode(self):
+        return self._mode
+
+    @property
+    def action_dim(self):
+        ext = (self.p1 == _lib.POLICY_EXTERNAL) + (self.p2 == _lib.POLICY_EXTERNAL)
+        return 4 * ext
+
+    def _info_dict(self, info):
+        return {"winner": info[:, 0], "reward_closeness_to_puck": info[:, 1], "reward_touch_puck": info[:, 2],
+                "reward_puck_direction": info[:, 3]}
+
+    # -- reference surface, batched ------------------------------------------------------------------
+    def reset(self, mask=None, one_starting=None):
+        """HockeyEnv.reset (hockey_env.py:345-418) for the envs selected by `mask` (bool/uint8 [N], None = all).
+        one_starting: None = alternate like the reference, bool, or int8 tensor [N] (1/0/-1)."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        o = None
+        if one_starting is not None:
+            if isinstance(one_starting, (bool, int)):
+                o = torch.full((self.num_envs,), int(bool(one_starting)), dtype=torch.int8, device=self.device)
+            else:
+                o = torch.as_tensor(one_starting, device=self.device).to(torch.int8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_reset(self._h, _ptr(m), _ptr(o), None, self._stream()))
+            _lib.check(self.L.hk_get_obs(self._h, _ptr(self.obs), _ptr(self.obs2), self._stream()))
+            _lib.check(self.L.hk_get_info(self._h, _ptr(self.info), _ptr(self.info2), self._stream()))
+        return self.obs, self._info_dict(self.info)
+
+    def step(self, action=None):
+        """HockeyEnv.step (hockey_env.py:658-695).  action: float32 CUDA tensor [N, 8] (both players), [N, 4]
+        (player 1 only, player 2 in-kernel) or None (both in-kernel).  Returns the reference's 5-tuple of
+        device tensors: obs [N,18], reward [N], done [N] (uint8), truncated [N] (all False), info dict."""
+        a, stride = None, 0
+        if self.p1 == _lib.POLICY_EXTERNAL or self.p2 == _lib.POLICY_EXTERNAL:
+            if action is None:
+                raise ValueError("step() needs an action tensor: at least one player is external")
+            a = action
+            if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()):
+                a = torch.as_tensor(action, dtype=torch.float32, device=self.device).contiguous()
+            if a.dim() != 2 or a.shape[0] != self.num_envs:
+                raise ValueError(f"action must be [num_envs, 4 or 8], got {tuple(a.shape)}")
+            stride = a.shape[1]
+            if self.p2 == _lib.POLICY_EXTERNAL and self.p1 != _lib.POLICY_EXTERNAL and stride == 4:
+                # only player 2 is external: its 4 columns are expected at offset 4
+                a = torch.cat([torch.zeros_like(a), a], dim=1).contiguous()
+                stride = 8
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_step(self._h, _ptr(a), stride, self.p1, self.p2,
+                                      _lib.STEP_AUTORESET if self.auto_reset else 0,
+                                      _ptr(self.obs), _ptr(self.obs2), _ptr(self.reward), _ptr(self.reward2),
+                                      _ptr(self.done), _ptr(self.info), _ptr(self.info2), _ptr(self.final_obs),
+                                      self._stream()))
+        return self.obs, self.reward, self.done, self.truncated, self._info_dict(self.info)
+
+    def rollout(self, k_steps, p1="strong", p2="strong", write_obs=False):
+        """k fused ticks in one launch with in-kernel policies and auto-reset (hk_rollout)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_rollout(self._h, int(k_steps), _policy_id(p1), _policy_id(p2),
+                                         _ptr(self.obs) if write_obs else None, self._stream()))
+
+    def obs_agent_two(self):
+        """hockey_env.py:500-516 for the current state."""
+        if self.obs2 is None:
+            self.obs2 = torch.empty((self.num_envs, 18), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_get_obs(self._h, None, _ptr(self.obs2), self._stream()))
+        return self.obs2
+
+    def get_info_agent_two(self):
+        """hockey_env.py:568-591 (needs want_agent_two=True so that the step kernel materialises it)."""
+        if self.info2 is None:
+            raise ValueError("construct HockeyVecEnv(want_agent_two=True) to get agent-two info/reward")
+        return self._info_dict(self.info2)
+
+    def get_reward(self, info=None):
+        return self.reward
+
+    def get_reward_agent_two(self, info_two=None):
+        if self.reward2 is None:
+            raise ValueError("construct HockeyVecEnv(want_agent_two=True) to get agent-two info/reward")
+        return self.reward2
+
+    def set_state(self, state):
+        """HockeyEnv.set_state (hockey_env.py:594-608): [N,18] visible values; hidden state untouched."""
+        s = torch.as_tensor(state, dtype=torch.float32, device=self.device).contiguous()
+        if s.shape != (self.num_envs, 18):
+            raise ValueError("state must be [num_envs, 18]")
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_set_obs_state(self._h, _ptr(s), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()  # `s` may be a temporary
+
+    def get_full_state(self):
+        """Superset of set_state: the canonical [N, STATE_WORDS] int32 record incl. hidden state."""
+        s = torch.empty((self.num_envs, _lib.STATE_WORDS), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_get_state(self._h, _ptr(s), self._stream()))
+        return s
+
+    def set_full_state(self, s):
+        s = torch.as_tensor(s, device=self.device).to(torch.int32).contiguous()
+        if s.shape != (self.num_envs, _lib.STATE_WORDS):
+            raise ValueError(f"state must be [num_envs, {_lib.STATE_WORDS}]")
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_set_state(self._h, _ptr(s), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def current_obs(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_get_obs(self._h, _ptr(self.obs), None, self._stream()))
+        return self.obs
+
+    def stats(self):
+        """Episode statistics accumulated on the device (include/hockey_b200.h hk_get_stats)."""
+        out = (C.c_double * _lib.STATS_DIM)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_get_stats(self._h, out, self._stream()))
+        v = np.array(out[:], dtype=np.float64)
+        keys = ["episodes", "wins", "losses", "draws", "env_steps", "sum_return_p1", "sum_return_p2", "sum_return_sq_p1",
+                "sum_episode_len", "touches_p1", "touches_p2", "velocity_iterations", "toi_events", "overflows"]
+        return dict(zip(keys, v.tolist()))
+
+    def stats_tensor(self):
+        """The device accumulators as a float64 tensor view-copy (for an NCCL all-reduce)."""
+        t = torch.empty(_lib.STATS_DIM, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_copy_stats(self._h, _ptr(t), self._stream()))
+        return t
+
+    def clear_stats(self):
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_clear_stats(self._h, self._stream()))
+
+    @staticmethod
+    def discrete_to_continous_action(discrete_action, keep_mode=True):
+        """hockey_env.py:637-656."""
+        a = [(discrete_action == 1) * -1.0 + (discrete_action == 2) * 1.0,
+             (discrete_action == 3) * -1.0 + (discrete_action == 4) * 1.0,
+             (discrete_action == 5) * -1.0 + (discrete_action == 6) * 1.0]
+        if keep_mode:
+            a.append((discrete_action == 7) * 1.0)
+        return a
+
+
+class _Box:
+    """Minimal stand-in for gymnasium.spaces.Box when gymnasium is not installed."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low = np.full(shape, low, dtype=dtype)
+        self.high = np.full(shape, high, dtype=dtype)
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+
+    def sample(self):
+        lo = np.where(np.isfinite(self.low), self.low, -1.0)
+        hi = np.where(np.isfinite(self.high), self.high, 1.0)
+        return np.random.uniform(lo, hi).astype(self.dtype)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+
+class _Discrete:
+    def __init__(self, n):
+        self.n = n
+
+    def sample(self):
+        return int(np.random.randint(self.n))
+
+
+try:  # use the real spaces when gymnasium exists (the reference subclasses gym.Env, hockey_env.py:83)
+    from gymnasium import spaces as _spaces
+    import gymnasium as _gym
+    _EnvBase = _gym.Env
+    _mkbox = lambda lo, hi, shape: _spaces.Box(lo, hi, shape=shape, dtype=np.float32)
+    _mkdisc = lambda n: _spaces.Discrete(n)
+except Exception:  # pragma: no cover - depends on the environment
+    _EnvBase = object
+    _mkbox = lambda lo, hi, shape: _Box(lo, hi, shape)
+    _mkdisc = lambda n: _Discrete(n)
+
+
+class HockeyEnv(_EnvBase):
+    """Drop-in for hockey.hockey_env.HockeyEnv (hockey_env.py:83-779): one env, numpy in / numpy out,
+    same constructor, same return shapes; physics runs in the CUDA library (batch of 1)."""
+
+    metadata = {"render.modes": ["human", "rgb_array"], "render_fps": FPS}
+    continuous = False
+
+    def __init__(self, keep_mode: bool = True, mode=Mode.NORMAL, verbose: bool = False, device="cuda:0", seed=None,
+                 _p2=None):
+        self.mode = mode
+        self.keep_mode = keep_mode
+        self.verbose = verbose
+        self.timeStep = 1.0 / FPS
+        self.done = False
+        self.winner = 0
+        self.closest_to_goal_dist = 1000
+        seed = int(np.random.SeedSequence().entropy % (1 << 63)) if seed is None else int(seed)
+        self._vec = HockeyVecEnv(1, mode=self._mode, keep_mode=keep_mode, device=device, seed=seed, auto_reset=False,
+                                 p2=_p2, want_agent_two=True)
+        self.max_timesteps = self._vec.max_timesteps
+        self.time = 0
+        self.one_starts = True
+        obs_dim = 18 if keep_mode else 16
+        self.observation_space = _mkbox(-np.inf, np.inf, (obs_dim,))
+        self.num_actions = 3 if not keep_mode else 4
+        self.action_space = _mkbox(-1, +1, (self.num_actions * 2,))
+        self.discrete_action_space = _mkdisc(7)
+        self._info = None
+        self._info2 = None
+
+    # mode property with the reference's accepted forms and errors (hockey_env.py:754-779)
+    @property
+    def mode(self):
+        return self._mode
+
+    @mode.setter
+    def mode(self, value):
+        self._mode = _as_mode(value)
+
+    def seed(self, seed=None):
+        return [seed]
+
+    def _obs_np(self, t):
+        o = t[0].detach().cpu().numpy().astype(np.float64)  # the reference returns float64 (np.hstack)
+        return o if self.keep_mode else o[:16]
+
+    def _info_np(self, t):
+        v = t[0].detach().cpu().numpy()
+        return {"winner": int(v[0]), "reward_closeness_to_puck": float(v[1]), "reward_touch_puck": float(v[2]),
+                "reward_puck_direction": float(v[3])}
+
+    def reset(self, one_starting=None, mode=None, seed=None, options=None):
+        if mode is not None and _as_mode(mode) != self._mode:
+            raise ValueError("the mode of a HockeyEnv is fixed at construction in this implementation")
+        if self._mode == Mode.NORMAL:
+            self.one_starts = bool(one_starting) if one_starting is not None else (not self.one_starts)
+        self._vec.reset(one_starting=self.one_starts if self._mode == Mode.NORMAL else None)
+        self.done = False
+        self.winner = 0
+        self.time = 0
+        self.closest_to_goal_dist = 1000
+        obs = self._obs_np(self._vec.obs)
+        self._info = self._info_np(self._vec.info)
+        self._info2 = self._info_np(self._vec.info2)
+        return obs, dict(self._info)
+
+    def _pad_action(self, action):
+        a = np.clip(np.asarray(action, dtype=np.float64), -1, +1).astype(np.float32)
+        if not self.keep_mode:  # 3 per player -> 4 per player with shoot = 0
+            a = np.concatenate([a[0:3], [0.0], a[3:6], [0.0]]).astype(np.float32)
+        return a
+
+    def step(self, action):
+        a = self._pad_action(action)
+        at = torch.from_numpy(a.reshape(1, -1)).to(self._vec.device)
+        obs, reward, done, _, _ = self._vec.step(at)
+        self._info = self._info_np(self._vec.info)
+        self._info2 = self._info_np(self._vec.info2)
+        self._reward2 = float(self._vec.reward2[0].item())
+        self.done = bool(done[0].item())
+        self.winner = self._info["winner"]
+        self.time += 1
+        return self._obs_np(obs), float(reward[0].item()), self.done, False, dict(self._info)
+
+    def obs_agent_two(self):
+        return self._obs_np(self._vec.obs_agent_two())
+
+    def get_info_agent_two(self):
+        return dict(self._info2)
+
+    def _compute_reward(self):
+        r = 0
+        if self.done:
+            if self.winner == 1:
+                r += 10
+            elif self.winner == -1:
+                r -= 10
+        return float(r)
+
+    def get_reward(self, info):
+        return float(self._compute_reward() + info["reward_closeness_to_puck"])
+
+    def get_reward_agent_two(self, info_two):
+        return float(-self._compute_reward() + info_two["reward_closeness_to_puck"])
+
+    def set_state(self, state):
+        s = np.zeros(18, dtype=np.float64)
+        st = np.asarray(state, dtype=np.float64)
+        s[:len(st)] = st
+        self._vec.set_state(torch.from_numpy(s.astype(np.float32).reshape(1, 18)))
+
+    def discrete_to_continous_action(self, discrete_action):
+        return HockeyVecEnv.discrete_to_continous_action(discrete_action, self.keep_mode)
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering (pygame, hockey_env.py:697-744) is out of scope of the B200 hot path")
+
+    def close(self):
+        self._vec.close()
+
+
+class BasicOpponent:
+    """hockey_env.py:781-833.  `act` accepts one observation (numpy, reference behaviour incl. the global
+    numpy RNG) or a batch [N,18] torch tensor (vectorised on the tensor's device)."""
+
+    def __init__(self, weak=True, keep_mode=True):
+        self.weak = weak
+        self.keep_mode = keep_mode
+        self.phase = np.random.uniform(0, np.pi)
+
+    def act(self, obs, verbose=False):
+        if isinstance(obs, torch.Tensor) and obs.dim() == 2:
+            return self._act_batch(obs)
+        obs = np.asarray(obs, dtype=np.float64)
+        alpha = obs[2]
+        p1 = np.asarray([obs[0], obs[1], alpha])
+        v1 = np.asarray(obs[3:6])
+        puck = np.asarray(obs[12:14])
+        puckv = np.asarray(obs[14:16])
+        target_pos = p1[0:2]
+        self.phase += np.random.uniform(0, 0.2)
+        time_to_break = 0.1
+        kp = 0.5 if self.weak else 10
+        kd = 0.5
+        if puckv[0] < 30.0 / SCALE:
+            dist = np.sqrt(np.sum((p1[0:2] - puck) ** 2))
+            if p1[0] < puck[0] and abs(p1[1] - puck[1]) < 30.0 / SCALE:
+                target_pos = [puck[0] + 0.2, puck[1] + puckv[1] * dist * 0.1]
+            else:
+                target_pos = [-210 / SCALE, puck[1]]
+        else:
+            target_pos = [-210 / SCALE, 0]
+        target_angle = MAX_ANGLE * np.sin(self.phase)
+        shoot = 0.0
+        if self.keep_mode and obs[16] > 0 and obs[16] < 7:
+            shoot = 1.0
+        target = np.asarray([target_pos[0], target_pos[1], target_angle])
+        error = target - p1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            need_break = abs((error / (v1 + 0.01))) < [time_to_break, time_to_break, time_to_break * 10]
+        action = np.clip(error * [kp, kp / 5, kp / 2] - v1 * need_break * [kd, kd, kd], -1, 1)
+        if self.keep_mode:
+            return np.hstack([action, [shoot]])
+        return action
+
+    def _act_batch(self, obs):
+        n = obs.shape[0]
+        o = obs.to(torch.float64)
+        if not isinstance(self.phase, torch.Tensor) or self.phase.shape[0] != n:
+            self.phase = torch.rand(n, dtype=torch.float64, device=obs.device) * math.pi
+        self.phase = self.phase + torch.rand(n, dtype=torch.float64, device=obs.device) * 0.2
+        kp = 0.5 if self.weak else 10.0
+        kd = 0.5
+        p1 = o[:, 0:3]
+        v1 = o[:, 3:6]
+        puck = o[:, 12:14]
+        puckv = o[:, 14:16]
+        dist = torch.sqrt(((p1[:, 0:2] - puck) ** 2).sum(1))
+        toward = puckv[:, 0] < 30.0 / SCALE
+        behind = (p1[:, 0] < puck[:, 0]) & ((p1[:, 1] - puck[:, 1]).abs() < 30.0 / SCALE)
+        tx = torch.where(toward & behind, puck[:, 0] + 0.2, torch.full_like(dist, -210 / SCALE))
+        ty = torch.where(toward, torch.where(behind, puck[:, 1] + puckv[:, 1] * dist * 0.1, puck[:, 1]), torch.zeros_like(dist))
+        ta = MAX_ANGLE * torch.sin(self.phase)
+        target = torch.stack([tx, ty, ta], 1)
+        error = target - p1
+        ttb = torch.tensor([0.1, 0.1, 1.0], dtype=torch.float64, device=obs.device)
+        need_break = ((error / (v1 + 0.01)).abs() < ttb).to(torch.float64)
+        kps = torch.tensor([kp, kp / 5, kp / 2], dtype=torch.float64, device=obs.device)
+        action = torch.clamp(error * kps - v1 * need_break * kd, -1, 1)
+        if self.keep_mode:
+            shoot = ((o[:, 16] > 0) & (o[:, 16] < 7)).to(torch.float64)
+            action = torch.cat([action, shoot[:, None]], 1)
+        return action.to(torch.float32)
+
+
+class HockeyEnv_BasicOpponent(HockeyEnv):
+    """hockey_env.py:875-886: player 2 is a BasicOpponent; here it runs inside the step kernel."""
+
+    def __init__(self, mode=Mode.NORMAL, weak_opponent=False, device="cuda:0", seed=None):
+        super().__init__(mode=mode, keep_mode=True, device=device, seed=seed, _p2="weak" if weak_opponent else "strong")
+        self.opponent = BasicOpponent(weak=weak_opponent)  # API compatibility; acting happens in-kernel
+        self.action_space = _mkbox(-1, +1, (4,))
+
+    def step(self, action):
+        a = np.clip(np.asarray(action, dtype=np.float64), -1, +1).astype(np.float32)
+        at = torch.from_numpy(a.reshape(1, 4)).to(self._vec.device)
+        obs, reward, done, _, _ = self._vec.step(at)
+        self._info = self._info_np(self._vec.info)
+        self._info2 = self._info_np(self._vec.info2)
+        self.done = bool(done[0].item())
+        self.winner = self._info["winner"]
+        self.time += 1
+        return self._obs_np(obs), float(reward[0].item()), self.done, False, dict(self._info)
+
+
+class PolicyOpponent:
+    """hockey_env.py:908-922: wraps a torch policy as act(obs) -> np.array of 4 actions."""
+
+    def __init__(self, policy, device=None):
+        self.policy = policy
+        self.device = device
+
+    def act(self, obs):
+        with torch.no_grad():
+            x = torch.tensor(obs, dtype=torch.float32, device=self.device).unsqueeze(0)
+            a = self.policy(x).squeeze(0).cpu().numpy()
+        return a

@@ -128,6 +128,10 @@ int hk_rollout(hk_env* env, int k_steps, int p1_policy, int p2_policy, float* ob
 /* Observations of the current state without stepping (_get_obs / obs_agent_two, hockey_env.py:485-516). */
 int hk_get_obs(hk_env* env, float* obs_dev, float* obs2_dev, void* stream);
 
+/* _get_info / get_info_agent_two of the current state without stepping (what reset() returns,
+ * hockey_env.py:416-418, 542-591).  info_dev / info2_dev: f32 [n,4], nullable. */
+int hk_get_info(hk_env* env, float* info_dev, float* info2_dev, void* stream);
+
 /* Superset of HockeyEnv.set_state (hockey_env.py:594-608): the full record incl. hidden state. */
 int hk_get_state(hk_env* env, uint32_t* state_dev /* [n, HK_STATE_WORDS] */, void* stream);
 int hk_set_state(hk_env* env, const uint32_t* state_dev, void* stream);
@@ -143,6 +147,8 @@ int hk_get_stats(hk_env* env, double* out_host, void* stream);
 int hk_clear_stats(hk_env* env, void* stream);
 /* Device pointer to the HK_STATS_DIM accumulators (f64), for an NCCL all-reduce without a host hop. */
 int hk_stats_device_ptr(hk_env* env, double** out_dev);
+/* Device-to-device copy of the accumulators into a caller-owned f64[HK_STATS_DIM] buffer (async). */
+int hk_copy_stats(hk_env* env, double* dst_dev, void* stream);
 
 const char* hk_last_error(void);
 const char* hk_version(void);

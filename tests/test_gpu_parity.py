@@ -1,0 +1,193 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via hockey_env_b200) against the CPU oracle.
+
+Bar (north_star): identical results on identical inputs.  Because the library is built without FMA
+contraction and with reproducible trig, the comparison here is EXACT on the full state record and on every
+output (float words compared numerically so that -0.0 == +0.0), not merely within 1e-4.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _mk(hk, O, n, mode, seed, p1, p2, **kw):
+    names = {O.POL_EXTERNAL: None, O.POL_WEAK: "weak", O.POL_STRONG: "strong", O.POL_RANDOM: "random", O.POL_ZERO: "zero"}
+    env = hk.HockeyVecEnv(n, mode=hk.Mode(mode), device="cuda:0", seed=seed, p1=names[p1], p2=names[p2],
+                          want_agent_two=True, **kw)
+    ora = O.OracleBatch(n, mode=mode, seed=seed, env_id_offset=kw.get("env_id_offset", 0), n_threads=8)
+    return env, ora
+
+
+def _state(env):
+    return env.get_full_state().cpu().numpy().view(np.uint32)
+
+
+def _compare_step(env, ro, t):
+    for k, ten in (("obs", env.obs), ("obs2", env.obs2), ("done", env.done), ("final_obs", env.final_obs)):
+        assert np.array_equal(ten.cpu().numpy(), ro[k]), f"{k} differs at tick {t}"
+    for k, ten in (("reward", env.reward), ("reward2", env.reward2), ("info", env.info), ("info2", env.info2)):
+        assert np.array_equal(ten.cpu().numpy(), ro[k].astype(np.float32)), f"{k} differs at tick {t}"
+
+
+@pytest.mark.parametrize("mode,p1,p2,steps", [
+    (0, 2, 2, 400),   # NORMAL strong vs strong (BASELINE config 4 / headline)
+    (0, 1, 2, 300),   # NORMAL weak vs strong (config 1)
+    (1, 3, 3, 200),   # TRAIN_SHOOTING random actions (config 2)
+    (2, 2, 4, 200),   # TRAIN_DEFENSE strong vs zero (config 3, notebook cell 20 setup)
+    (2, 2, 1, 200),   # TRAIN_DEFENSE strong vs weak
+])
+def test_fused_policies_full_state_parity(oracle, mode, p1, p2, steps):
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    env, ora = _mk(hk, O, 256, mode, 77 + mode, p1, p2, env_id_offset=5_000_000_000)
+    assert len(state_mismatches(ora.get_state(), _state(env))) == 0
+    for t in range(steps):
+        env.step()
+        ro = ora.step(None, p1, p2, O.STEP_AUTORESET)
+        _compare_step(env, ro, t)
+        if t % 25 == 0 or t == steps - 1:
+            bad = state_mismatches(ora.get_state(), _state(env))
+            assert len(bad) == 0, f"state differs at tick {t}: {bad[:8].tolist()}"
+    s, so = env.stats(), ora.stats()
+    assert s["overflows"] == 0
+    for k, i in (("episodes", 0), ("wins", 1), ("losses", 2), ("draws", 3), ("env_steps", 4), ("toi_events", 12)):
+        assert s[k] == so[i], k
+    assert s["episodes"] > 0
+
+
+def test_external_actions_and_no_autoreset(oracle):
+    """HockeyEnv.step with caller-supplied [N,8] actions (incl. values outside [-1,1], clipped as hockey_env.py:659)
+    and stepping after done (the reference has no guard)."""
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    n = 128
+    env = hk.HockeyVecEnv(n, mode=hk.Mode.TRAIN_SHOOTING, device="cuda:0", seed=5, auto_reset=False, want_agent_two=True)
+    ora = O.OracleBatch(n, mode=1, seed=5)
+    rng = np.random.default_rng(0)
+    for t in range(120):  # past the 81-tick limit
+        a = rng.uniform(-1.4, 1.4, (n, 8)).astype(np.float32)
+        env.step(torch.from_numpy(a).cuda())
+        ro = ora.step(a, O.POL_EXTERNAL, O.POL_EXTERNAL, 0)
+        for k, ten in (("obs", env.obs), ("done", env.done)):
+            assert np.array_equal(ten.cpu().numpy(), ro[k]), f"{k} differs at tick {t}"
+        assert np.array_equal(env.reward.cpu().numpy(), ro["reward"].astype(np.float32))
+    assert env.done.all()
+    assert len(state_mismatches(ora.get_state(), _state(env))) == 0
+
+
+def test_basic_opponent_wrapper_path(oracle):
+    """HockeyEnv_BasicOpponent.step semantic: [N,4] actions for player 1, in-kernel opponent for player 2."""
+    import hockey_env_b200 as hk
+    O = oracle
+    n = 128
+    env = hk.HockeyVecEnv(n, device="cuda:0", seed=9, p2="strong", want_agent_two=True)
+    ora = O.OracleBatch(n, mode=0, seed=9)
+    rng = np.random.default_rng(1)
+    for t in range(300):
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        env.step(torch.from_numpy(a).cuda())
+        ro = ora.step(a, O.POL_EXTERNAL, O.POL_STRONG, O.STEP_AUTORESET)
+        _compare_step(env, ro, t)
+
+
+def test_state_roundtrip_and_injection(oracle):
+    """hk_get_state / hk_set_state: a state taken from the oracle mid-game, injected into the CUDA env, evolves
+    identically (single-step transitions from identical states, incl. hidden state)."""
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    n = 256
+    ora = O.OracleBatch(n, mode=0, seed=21, n_threads=8)
+    for _ in range(137):
+        ora.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+    s = ora.get_state()
+    env = hk.HockeyVecEnv(n, device="cuda:0", seed=21, p1="strong", p2="strong", want_agent_two=True)
+    env.set_full_state(torch.from_numpy(s.view(np.int32)).cuda())
+    assert len(state_mismatches(s, _state(env))) == 0
+    for t in range(60):
+        env.step()
+        ro = ora.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+        _compare_step(env, ro, t)
+    assert len(state_mismatches(ora.get_state(), _state(env))) == 0
+
+
+def test_rollout_equals_steps(oracle):
+    """hk_rollout(k) == k x hk_step with the same in-kernel policies."""
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    n = 512
+    a = hk.HockeyVecEnv(n, device="cuda:0", seed=3, p1="strong", p2="weak")
+    b = hk.HockeyVecEnv(n, device="cuda:0", seed=3, p1="strong", p2="weak")
+    for _ in range(12):
+        a.rollout(16, "strong", "weak")
+        for _ in range(16):
+            b.step()
+    assert len(state_mismatches(_state(a), _state(b))) == 0
+    sa, sb = a.stats(), b.stats()
+    assert sa["env_steps"] == sb["env_steps"] == n * 192
+    assert sa["episodes"] == sb["episodes"] and sa["wins"] == sb["wins"]
+
+
+def test_golden_notebook_trace_gpu(oracle):
+    """The reference's only exact artefact (Hockey-Env.ipynb cell 20) through the CUDA path."""
+    import json
+    import os
+    import hockey_env_b200 as hk
+    O = oracle
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_fixtures.json")))
+    g = fx["train_defense_trace"]
+    ora = O.OracleBatch(1, mode=2, seed=0)
+    ora.reset_with_draws(0, g["reset_draws"])
+    env = hk.HockeyVecEnv(1, mode=hk.Mode.TRAIN_DEFENSE, device="cuda:0", seed=0, auto_reset=False)
+    env.set_full_state(torch.from_numpy(ora.get_state().view(np.int32)).cuda())
+    act = torch.tensor([g["action"]], dtype=torch.float32, device="cuda:0")
+    rewards, dones = [], []
+    for t in range(len(g["rewards"])):
+        _, r, d, _, _ = env.step(act)
+        rewards.append(float(r[0].item()))
+        dones.append(int(d[0].item()))
+    rewards = np.array(rewards)
+    gold = np.array(g["rewards"])
+    assert np.abs(rewards[:7] - gold[:7]).max() < 1.5e-7
+    assert abs(rewards[7] - gold[7]) < 1e-6
+    assert np.all(rewards[8:19] == 0.0) and rewards[19] == 10.0
+    assert dones[:19] == [0] * 19 and dones[19] == 1
+
+
+def test_single_env_drop_in_classes(oracle):
+    """HockeyEnv / HockeyEnv_BasicOpponent keep the reference's call shapes and types."""
+    import hockey_env_b200 as hk
+    env = hk.HockeyEnv(mode=hk.Mode.NORMAL, seed=4)
+    obs, info = env.reset()
+    assert obs.shape == (18,) and obs.dtype == np.float64
+    assert set(info) == {"winner", "reward_closeness_to_puck", "reward_touch_puck", "reward_puck_direction"}
+    p1, p2 = hk.BasicOpponent(weak=False), hk.BasicOpponent()
+    obs2 = env.obs_agent_two()
+    total = 0.0
+    for t in range(251):
+        a1, a2 = p1.act(obs), p2.act(obs2)
+        obs, r, d, trunc, info = env.step(np.hstack([a1, a2]))
+        assert isinstance(r, float) and isinstance(d, bool) and trunc is False
+        obs2 = env.obs_agent_two()
+        total += r
+        if d:
+            break
+    assert d and t <= 250
+    info2 = env.get_info_agent_two()
+    assert info2["winner"] == -info["winner"]
+    assert env.get_reward(info) == pytest.approx(r, abs=1e-6)
+    env.close()
+    e1 = hk.HockeyEnv_BasicOpponent(mode=0, weak_opponent=True, seed=1)
+    o, _ = e1.reset()
+    for _ in range(30):
+        o, r, d, _, _ = e1.step(np.array([1.0, 0.0, 0.0, 0.0]))
+    assert o[0] > -3.0 + 0.5  # player 1 moved right from x = -3
+    e1.close()
+    with pytest.raises(ValueError):
+        hk.HockeyEnv(mode="NOPE")
+    with pytest.raises(TypeError):
+        hk.HockeyEnv(mode=1.5)

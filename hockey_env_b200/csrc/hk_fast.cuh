@@ -1,0 +1,235 @@
+// hk_fast.cuh -- the contact-free fast path of one world step.
+//
+// Most env-ticks have nothing to solve: no solid contact touches and no continuous-collision event
+// can occur.  worldStepFast() proves that cheaply and then does exactly what the general worldStep()
+// would do in that case (integrate, sync proxies, find new contacts, sleep bookkeeping).  If the
+// proof fails at any point it returns false WITHOUT side effects that matter: the caller discards
+// the working copy and queues the env for the general path (hk_world.cuh), which redoes the tick
+// from the stored state.  A fast tick never writes the warm-start cache.
+//
+// The proofs are conservative bounds with a margin far above float rounding:
+//  * polygon-polygon manifold is empty if the incident polygon lies beyond an axis-aligned face of
+//    the (axis-aligned or trapezoid) static polygon by more than totalRadius + eps: every static
+//    polygon of the scene has +-x face normals and the boxes also +-y, and b2CollidePolygons returns
+//    no points as soon as the max face separation exceeds totalRadius;
+//  * a sensor does not overlap if the puck centre is farther than r + skin + eps from the goal box;
+//  * b2TimeOfImpact can only report "touching" if the core shapes come within target + tolerance at
+//    some time of the sweep; if the swept core AABB of the moving shape stays farther than that (plus
+//    the chord-to-arc sagitta of the rotation and eps) from the static core AABB, alpha is 1.
+#pragma once
+#include "hk_world.cuh"
+
+namespace hk {
+
+#define HK_FAST_EPS 0.005f
+#if defined(HK_FAST_DEBUG) && !defined(__CUDA_ARCH__)
+extern long long g_fast_bail[16];
+#define HK_BAIL(k) do { g_fast_bail[k]++; return false; } while (0)
+#else
+#define HK_BAIL(k) return false
+#endif
+
+HK_HD AABB staticCoreAABB(const Scene& S, int f) {  // fat box minus extension and skin (exact enough: eps >> rounding)
+  AABB r = S.sfat[f];
+  const float d = HK_AABB_EXTENSION + HK_POLYGON_RADIUS;
+  r.lx += d;
+  r.ly += d;
+  r.hx -= d;
+  r.hy -= d;
+  return r;
+}
+HK_HD float aabbGap(const AABB& a, const AABB& b) {
+  float gx = fmax2(a.lx - b.hx, b.lx - a.hx);
+  float gy = fmax2(a.ly - b.hy, b.ly - a.hy);
+  return fmax2(gx, gy);
+}
+// gap restricted to the face normals the static polygon really has (+-x always; +-y for boxes f<2, f>=6;
+// corner trapezoids: only the outward y face: -y for bottom ones (3,5), +y for top ones (2,4))
+HK_HD float staticFaceGap(int f, const AABB& a /*static core*/, const AABB& b /*moving core*/) {
+  float g = fmax2(b.lx - a.hx, a.lx - b.hx);
+  bool hasUp = f < 2 || f >= 6 || f == 2 || f == 4;
+  bool hasDown = f < 2 || f >= 6 || f == 3 || f == 5;
+  if (hasUp) g = fmax2(g, b.ly - a.hy);
+  if (hasDown) g = fmax2(g, a.ly - b.hy);
+  return g;
+}
+
+struct FastScratch {
+  AABB swept[3];  // tight swept AABB (with shape radius) from this tick's synchronizeFixtures
+};
+
+HK_HD bool collideFast(const Scene& S, const Config& cfg, Env& e) {
+  int i = 0;
+  while (i < e.ncontacts) {
+    int pid = clistGet(e.clist, i);
+    const uint32_t bit = 1u << pid;
+    int fA = S.pairFA[pid], fB = S.pairFB[pid];
+    int bA = fixtureBody(fA), bB = fixtureBody(fB);
+    bool activeA = bA >= 0 && e.b[bA].awake;
+    bool activeB = bB >= 0 && e.b[bB].awake;
+    if (!activeA && !activeB) {
+      // a sleeping pair that still touches would have to be solved if something wakes it: not a fast tick
+      if ((e.touch & bit) && !(HK_PAIRS_SENSOR & bit)) HK_BAIL(1);
+      ++i;
+      continue;
+    }
+    if (!aabbOverlap(fixtureFat(S, e, fA), fixtureFat(S, e, fB))) {
+      clistRemoveAt(e, i);
+      e.exist &= ~bit;
+      e.touch &= ~bit;
+      setCount(e, pid, 0);
+      continue;
+    }
+    e.enabled |= bit;
+    const bool wasTouching = (e.touch & bit) != 0;
+    bool touching;
+    if (HK_PAIRS_SENSOR & bit) {
+      AABB a = staticCoreAABB(S, fA);
+      V2 c = e.b[B_PUCK].p;
+      AABB pb;
+      pb.lx = pb.hx = c.x;
+      pb.ly = pb.hy = c.y;
+      float gap = aabbGap(a, pb);
+      if (gap > S.puckRadius + HK_POLYGON_RADIUS + HK_FAST_EPS) touching = false;
+      else HK_BAIL(2);  // needs the GJK test
+    } else if (fB == F_PUCK) {
+      Manifold m;
+      collidePolygonCircle(&m, S.poly[fA], fixtureXf(S, e, fA), e.b[B_PUCK].p, S.puckRadius);
+      if (m.count > 0) HK_BAIL(3 + (fA >= F_R1 ? 1 : 0));
+      touching = false;
+    } else {
+      if (bA >= 0) HK_BAIL(5);  // racket x racket: general path
+      AABB a = staticCoreAABB(S, fA);
+      AABB b = shapeAABB(S, bB, bodyXf(e.b[bB]));
+      b.lx += HK_POLYGON_RADIUS;
+      b.ly += HK_POLYGON_RADIUS;
+      b.hx -= HK_POLYGON_RADIUS;
+      b.hy -= HK_POLYGON_RADIUS;
+      if (staticFaceGap(fA, a, b) > 2.0f * HK_POLYGON_RADIUS + HK_FAST_EPS) touching = false;
+      else HK_BAIL(6);
+    }
+    if (!(HK_PAIRS_SENSOR & bit)) {
+      setCount(e, pid, 0);
+      if (touching != wasTouching) {
+        if (bA >= 0) setAwake(e.b[bA], true);
+        if (bB >= 0) setAwake(e.b[bB], true);
+      }
+    }
+    if (touching) e.touch |= bit; else e.touch &= ~bit;
+    if (!wasTouching && touching) beginContact(cfg, e, pid);
+    ++i;
+  }
+  return true;
+}
+
+// synchronizeFixtures that also keeps the tight swept box; q0 = rotation at the sweep start (== b.q before the move)
+HK_HD void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot q0, AABB* keep) {
+  Body& b = e.b[bi];
+  Xf xf1;
+  xf1.q = q0;
+  xf1.p = b.c0 - mul(xf1.q, mk(S.lcx[bi], S.lcy[bi]));
+  AABB a1 = shapeAABB(S, bi, xf1);
+  AABB a2 = shapeAABB(S, bi, bodyXf(b));
+  AABB comb;
+  comb.lx = fmin2(a1.lx, a2.lx);
+  comb.ly = fmin2(a1.ly, a2.ly);
+  comb.hx = fmax2(a1.hx, a2.hx);
+  comb.hy = fmax2(a1.hy, a2.hy);
+  *keep = comb;
+  moveProxy(e, bi, comb, b.p - xf1.p);
+}
+
+HK_HD bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float h) {
+  e.enabled = 0xFFFFFFFFu;
+  e.nmf = 0;
+  if (e.moved & 8u) {
+    e.moved &= ~8u;
+    findNewContacts(S, e);
+  }
+  if (!collideFast(S, cfg, e)) return false;
+  // ---- b2World::Solve with no constraints: every awake body is its own island ----
+  FastScratch fs;
+  Rot q0[3];
+  for (int bi = 2; bi >= 0; --bi) {
+    Body& b = e.b[bi];
+    b.island = false;
+    if (!b.awake) continue;
+    b.island = true;
+    q0[bi] = b.q;
+    b.c0 = b.c;
+    b.a0 = b.a;
+    b.v += h * (1.0f * mk(0.0f, 0.0f) + S.invMass[bi] * b.f);
+    b.w += h * S.invI[bi] * b.tq;
+    b.v *= fclamp(1.0f - h * b.ldamp, 0.0f, 1.0f);
+    b.w *= fclamp(1.0f - h * b.adamp, 0.0f, 1.0f);
+    integratePosition(b, h);
+    syncTransform(S, b, bi);
+    const float linTolSqr = HK_LINEAR_SLEEP_TOL * HK_LINEAR_SLEEP_TOL;
+    const float angTolSqr = HK_ANGULAR_SLEEP_TOL * HK_ANGULAR_SLEEP_TOL;
+    float minSleepTime;
+    if (b.w * b.w > angTolSqr || dot(b.v, b.v) > linTolSqr) {
+      b.sleep = 0.0f;
+      minSleepTime = 0.0f;
+    } else {
+      b.sleep += h;
+      minSleepTime = fmin2(HK_MAXFLOAT, b.sleep);
+    }
+    if (minSleepTime >= HK_TIME_TO_SLEEP) setAwake(b, false);
+  }
+  for (int bi = 2; bi >= 0; --bi)
+    if (e.b[bi].island) synchronizeFixturesKeep(S, e, bi, q0[bi], &fs.swept[bi]);
+  findNewContacts(S, e);
+  // ---- b2World::SolveTOI: prove alpha == 1 for every candidate ----
+  uint32_t cand = e.exist & HK_PAIRS_TOI;
+  if (cand) {
+    for (int i = 0; i < e.ncontacts; ++i) {
+      int pid = clistGet(e.clist, i);
+      if (!((cand >> pid) & 1u)) continue;
+      int fA = S.pairFA[pid], fB = S.pairFB[pid];
+      int bi = fB - F_R1;
+      const Body& B = e.b[bi];
+      if (!B.awake) continue;
+      if (!B.island) HK_BAIL(7);  // woken after the solve (new contact): its sweep is stale, take the general path
+      float r = bi == B_PUCK ? S.puckRadius : HK_POLYGON_RADIUS;
+      AABB mv = fs.swept[bi];
+      mv.lx += r;
+      mv.ly += r;
+      mv.hx -= r;
+      mv.hy -= r;
+      float da = fabs2(B.a - B.a0);
+      if (bi != B_PUCK && da > 0.2f) HK_BAIL(8);
+      float sag = bi == B_PUCK ? 0.0f : 0.0625f * da * da;  // |r| <= 0.5 m from the centre of mass: |r| da^2 / 8
+      float totalRadius = HK_POLYGON_RADIUS + r;
+      float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
+      float need = target + 0.25f * HK_LINEAR_SLOP + sag + HK_FAST_EPS;
+      if (!(aabbGap(staticCoreAABB(S, fA), mv) > need)) HK_BAIL(9 + (bi == B_PUCK ? 1 : 0));
+    }
+  }
+  for (int bi = 0; bi < 3; ++bi) {
+    e.b[bi].f = mk(0.0f, 0.0f);
+    e.b[bi].tq = 0.0f;
+  }
+  return true;
+}
+
+// fast variant of envStep: returns false if the tick needs the general path (e is then garbage)
+HK_HD bool envStepFast(const Scene& S, const Config& cfg, Env& e, const float action[8]) {
+  Body &p1 = e.b[B_R1], &p2 = e.b[B_R2], &puck = e.b[B_PUCK];
+  if (cfg.keep_mode && (e.has1 > 1 || e.has2 > 1)) HK_BAIL(0);  // keep/shoot ticks always have a deep contact
+  applyTranslation(S, p1, B_R1, action[0], action[1], true);
+  applyRotation(S, p1, B_R1, action[2]);
+  applyTranslation(S, p2, B_R2, action[4], action[5], false);
+  applyRotation(S, p2, B_R2, action[6]);
+  {
+    double vx = puck.v.x, vy = puck.v.y;
+    double puck_speed = sqrt(vx * vx + vy * vy);
+    puck.ldamp = puck_speed > HK_MAX_PUCK_SPEED ? 10.0f : 0.05f;
+  }
+  if (!worldStepFast(S, cfg, e, (float)(1.0 / HK_FPS))) return false;
+  if (e.time >= cfg.max_timesteps) e.done = true;
+  e.time += 1;
+  ++e.tick;
+  return true;
+}
+
+}  // namespace hk

@@ -10,6 +10,7 @@
 // library: without a CUDA device hk_create fails with HK_E_NODEVICE.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -107,10 +108,14 @@ struct KParams {
   float4* core;
   uint32_t* cache;
   double* stats;
+  int32_t* queue;    // env indices that need the general path this tick
+  uint32_t* qctl;    // [0] queue length, [1] slow-kernel blocks finished
   int64_t n;
   int64_t env_id_offset;
   Config cfg;
 };
+
+constexpr int kSlowBlock = 64;
 
 __global__ void __launch_bounds__(kBlock) k_create(KParams P) {
   __shared__ Scene S;
@@ -155,6 +160,69 @@ __global__ void __launch_bounds__(kBlock) k_step(KParams P, StepIO io) {
     storeEnv(P.core, P.n, i, e);
   }
   flushStats(P.stats, st);
+}
+
+// ---- the per-tick pipeline: k_fast over all envs, then k_slow over the queue k_fast produced ----------------
+// k_fast proves "nothing to solve" per env (hk_fast.cuh) and finishes those ticks with a small register
+// footprint; every other env index is appended to the queue (one atomic per warp).  k_slow runs the general
+// path on the compacted queue, so lanes that iterate the contact solver sit next to each other instead of
+// idling 30 neighbours (ncu, round 1: 1.6 active lanes per solver instruction before the split).
+__global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
+  __shared__ Scene S;
+  stageScene(&S);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < P.n;
+  TickStats st;
+  tickStatsZero(st);
+  bool ok = false;
+  if (valid) {
+    Env e;
+    loadEnv(P.core, P.n, i, e);
+    ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st);
+    if (ok) storeEnv(P.core, P.n, i, e);
+    else tickStatsZero(st);
+  }
+  const bool need = valid && !ok;
+  const unsigned m = __ballot_sync(0xffffffffu, need);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&P.qctl[0], (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) P.queue[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+  }
+  flushStats(P.stats, st);
+}
+
+__global__ void __launch_bounds__(kSlowBlock) k_slow(KParams P, StepIO io) {
+  __shared__ Scene S;
+  stageScene(&S);
+  const unsigned count = *((volatile uint32_t*)&P.qctl[0]);
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  TickStats st;
+  tickStatsZero(st);
+  if (j < (int64_t)count) {
+    const int64_t i = P.queue[j];
+    Env e;
+    loadEnv(P.core, P.n, i, e);
+    Cache cache;
+    cache.base = P.cache + i;
+    cache.stride = (size_t)P.n;
+    envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st);
+    storeEnv(P.core, P.n, i, e);
+  }
+  if ((int64_t)blockIdx.x * blockDim.x < (int64_t)count) flushStats(P.stats, st);
+  // the last block to finish re-arms the queue for the next tick
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned t = atomicAdd(&P.qctl[1], 1u);
+    if (t == gridDim.x - 1) {
+      P.qctl[0] = 0;
+      P.qctl[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // K fused ticks: body state stays in registers/local memory across ticks, HBM state traffic is paid once
@@ -252,17 +320,23 @@ struct hk_env {
   float4* core;
   uint32_t* cache;
   double* stats;
+  int32_t* queue;
+  uint32_t* qctl;
+  bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
     KParams P;
     P.core = core;
     P.cache = cache;
     P.stats = stats;
+    P.queue = queue;
+    P.qctl = qctl;
     P.n = n;
     P.env_id_offset = env_id_offset;
     P.cfg = cfg;
     return P;
   }
   unsigned grid() const { return (unsigned)((n + kBlock - 1) / kBlock); }
+  unsigned gridSlow() const { return (unsigned)((n + kSlowBlock - 1) / kSlowBlock); }
 };
 
 static bool validPolicy(int p) { return p >= HK_POLICY_EXTERNAL && p <= HK_POLICY_ZERO; }
@@ -295,6 +369,12 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   h->core = nullptr;
   h->cache = nullptr;
   h->stats = nullptr;
+  h->queue = nullptr;
+  h->qctl = nullptr;
+  {
+    const char* m = getenv("HK_MONO");
+    h->mono = m && m[0] == '1';
+  }
   Scene S;
   std::memset(&S, 0, sizeof(S));
   scene_build::build(&S);
@@ -302,6 +382,9 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->cache, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->stats, sizeof(double) * HK_STATS_DIM);
+  if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * (size_t)n_envs);
+  if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 2);
+  if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 2);
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
   if (err == cudaSuccess) {
@@ -314,6 +397,8 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     cudaFree(h->core);
     cudaFree(h->cache);
     cudaFree(h->stats);
+    cudaFree(h->queue);
+    cudaFree(h->qctl);
     delete h;
     return fail(HK_E_CUDA, msg);
   }
@@ -327,6 +412,8 @@ int hk_destroy(hk_env* h) {
   cudaFree(h->core);
   cudaFree(h->cache);
   cudaFree(h->stats);
+  cudaFree(h->queue);
+  cudaFree(h->qctl);
   delete h;
   return HK_OK;
 }
@@ -367,7 +454,12 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
   io.info = info_dev;
   io.info2 = info2_dev;
   io.final_obs = final_obs_dev;
-  k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+  if (h->mono) {
+    k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+  } else {
+    k_fast<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+    k_slow<<<h->gridSlow(), kSlowBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+  }
   HK_CUDA(cudaGetLastError());
   return HK_OK;
 }

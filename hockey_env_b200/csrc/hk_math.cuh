@@ -150,11 +150,19 @@ HK_HD V2 mulT(const Xf& T, V2 v) {
 struct Sweep {
   V2 lc, c0, c;
   float a0, a, alpha0;
+  bool rot;  // false: static body or the puck -- the rotation never enters a result (angle 0 resp. circle
+             // centred on the body origin with localCenter 0), so the sin/cos evaluation is skipped
 };
+HK_HD Rot rotIdentity() {
+  Rot q;
+  q.s = 0.0f;
+  q.c = 1.0f;
+  return q;
+}
 HK_HD void sweepXf(const Sweep& s, Xf* xf, float beta) {
   xf->p = (1.0f - beta) * s.c0 + beta * s.c;
   float angle = (1.0f - beta) * s.a0 + beta * s.a;
-  xf->q = rotOf(angle);
+  xf->q = s.rot ? rotOf(angle) : rotIdentity();
   xf->p -= mul(xf->q, s.lc);
 }
 HK_HD void sweepAdvance(Sweep& s, float alpha) {

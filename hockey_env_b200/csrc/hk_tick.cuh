@@ -3,6 +3,7 @@
 // (reference hockey_env.py:658-695, :882-886) plus the batched API's auto-reset.
 #pragma once
 #include "hk_state.cuh"
+#include "hk_fast.cuh"
 
 namespace hk {
 
@@ -41,13 +42,10 @@ HK_HD void writeRow18(float* dst, const float* o) {
   }
 }
 
+// everything after the physics of a tick: info/reward, outputs, statistics, auto-reset
 // `write` = false suppresses all per-tick outputs (fused rollout, all but the last tick)
-HK_HD void envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e, uint64_t env_id, size_t i,
-                   const StepIO& io, bool write, TickStats& st) {
-  float a[8];
-  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
-  const int had1 = e.has1, had2 = e.has2;
-  envStep(S, cfg, cache, e, a);
+HK_HD void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io, bool write,
+                      TickStats& st, int had1, int had2) {
   double inf[4], inf2[4];
   getInfo(cfg, e, false, inf);
   getInfo(cfg, e, true, inf2);
@@ -103,6 +101,27 @@ HK_HD void envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e
       writeRow18(io.obs2 + 18 * i, o);
     }
   }
+}
+
+// general tick
+HK_HD void envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e, uint64_t env_id, size_t i,
+                   const StepIO& io, bool write, TickStats& st) {
+  float a[8];
+  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+  const int had1 = e.has1, had2 = e.has2;
+  envStep(S, cfg, cache, e, a);
+  tickFinish(S, cfg, e, env_id, i, io, write, st, had1, had2);
+}
+
+// fast tick: returns false (e unusable, nothing written) if the env needs the general path this tick
+HK_HD bool envTickFast(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io,
+                       bool write, TickStats& st) {
+  float a[8];
+  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+  const int had1 = e.has1, had2 = e.has2;
+  if (!envStepFast(S, cfg, e, a)) return false;
+  tickFinish(S, cfg, e, env_id, i, io, write, st, had1, had2);
+  return true;
 }
 
 // HockeyEnv.__init__ for one env (hockey_env.py:91-155): phases of the built-in controllers

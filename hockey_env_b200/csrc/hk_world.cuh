@@ -137,8 +137,11 @@ HK_HD void setLinearVelocity(Body& b, V2 v) {
   if (dot(v, v) > 0.0f) setAwake(b, true);
   b.v = v;
 }
+// b2Body::SynchronizeTransform.  The puck is a circle centred on its body origin with localCenter 0: its
+// rotation never enters any result, so its q stays the identity and no sin/cos is evaluated for it.
+HK_HD Rot rotForBody(int bi, float a) { return bi == B_PUCK ? rotIdentity() : rotOf(a); }
 HK_HD void syncTransform(const Scene& S, Body& b, int bi) {
-  b.q = rotOf(b.a);
+  b.q = rotForBody(bi, b.a);
   b.p = b.c - mul(b.q, mk(S.lcx[bi], S.lcy[bi]));
 }
 HK_HD Xf bodyXf(const Body& b) {
@@ -199,7 +202,7 @@ HK_HD void moveProxy(Env& e, int bi, const AABB& aabb, V2 displacement) {
 HK_HD void synchronizeFixtures(const Scene& S, Env& e, int bi) {
   Body& b = e.b[bi];
   Xf xf1;
-  xf1.q = rotOf(b.a0);
+  xf1.q = rotForBody(bi, b.a0);
   xf1.p = b.c0 - mul(xf1.q, mk(S.lcx[bi], S.lcy[bi]));
   AABB a1 = shapeAABB(S, bi, xf1);
   AABB a2 = shapeAABB(S, bi, bodyXf(b));
@@ -213,7 +216,7 @@ HK_HD void synchronizeFixtures(const Scene& S, Env& e, int bi) {
 // b2Body::SetTransform (puck teleport, hockey_env.py:619)
 HK_HD void setTransformPuck(const Scene& S, Env& e, V2 position) {
   Body& b = e.b[B_PUCK];
-  b.q = rotOf(b.a);
+  b.q = rotIdentity();
   b.p = position;
   b.c = mul(bodyXf(b), mk(S.lcx[B_PUCK], S.lcy[B_PUCK]));
   b.c0 = b.c;
@@ -427,7 +430,9 @@ struct BodyRef {  // position/velocity view of one side of a constraint (static 
   V2 v;
   float w;
   V2 lc;
+  bool rot;  // only rackets have a rotation that matters
 };
+HK_HD Rot rotIf(bool rot, float a) { return rot ? rotOf(a) : rotIdentity(); }
 HK_HD BodyRef bodyRef(const Scene& S, const Env& e, int fixture) {
   BodyRef r;
   if (fixture < N_STATIC_FIX) {
@@ -436,8 +441,10 @@ HK_HD BodyRef bodyRef(const Scene& S, const Env& e, int fixture) {
     r.v = mk(0.0f, 0.0f);
     r.w = 0.0f;
     r.lc = mk(0.0f, 0.0f);
+    r.rot = false;
   } else {
     int bi = fixture - F_R1;
+    r.rot = bi != B_PUCK;
     r.c = e.b[bi].c;
     r.a = e.b[bi].a;
     r.v = e.b[bi].v;
@@ -470,8 +477,8 @@ HK_HD void initConstraint(const Scene& S, const Env& e, int pid, int slot, bool 
   BodyRef A = bodyRef(S, e, fA), B = bodyRef(S, e, fB);
   float mA = vc->mA, mB = vc->mB, iA = vc->iA, iB = vc->iB;
   Xf xfA, xfB;
-  xfA.q = rotOf(A.a);
-  xfB.q = rotOf(B.a);
+  xfA.q = rotIf(A.rot, A.a);
+  xfB.q = rotIf(B.rot, B.a);
   xfA.p = A.c - mul(xfA.q, A.lc);
   xfB.p = B.c - mul(xfB.q, B.lc);
   V2 points[2];
@@ -671,8 +678,8 @@ HK_HD float solvePositionConstraint(const Scene& S, Env& e, int pid, const Manif
   float aA = A.a, aB = B.a;
   for (int j = 0; j < count; ++j) {
     Xf xfA, xfB;
-    xfA.q = rotOf(aA);
-    xfB.q = rotOf(aB);
+    xfA.q = rotIf(A.rot, aA);
+    xfB.q = rotIf(B.rot, aB);
     xfA.p = cA - mul(xfA.q, A.lc);
     xfB.p = cB - mul(xfB.q, B.lc);
     V2 normal, point;
@@ -731,16 +738,39 @@ HK_HD void integratePosition(Body& b, float h) {
   b.a += h * b.w;
 }
 
-// b2World::Solve: islands by DFS from (puck, racket2, racket1), each solved with b2Island::Solve
+// b2World::Solve.  Islands are found by Box2D's DFS from (puck, racket2, racket1); because islands share no
+// dynamic body they are solved here in ONE pass -- all velocity constraints in one Gauss-Seidel loop (an island
+// that has converged only sees no-op sweeps, so the result equals solving island after island), position
+// iterations with a per-island "done" mask (that loop is not a fixed-point iteration, so each island must stop
+// exactly where b2Island::Solve would).  One loop per env instead of one per island keeps the lanes of a warp
+// in the same loop at the same time.
+HK_HD void synchronizeFixturesQ0(const Scene& S, Env& e, int bi, Rot q0) {
+  Body& b = e.b[bi];
+  Xf xf1;
+  xf1.q = q0;
+  xf1.p = b.c0 - mul(xf1.q, mk(S.lcx[bi], S.lcy[bi]));
+  AABB a1 = shapeAABB(S, bi, xf1);
+  AABB a2 = shapeAABB(S, bi, bodyXf(b));
+  AABB comb;
+  comb.lx = fmin2(a1.lx, a2.lx);
+  comb.ly = fmin2(a1.ly, a2.ly);
+  comb.hx = fmax2(a1.hx, a2.hx);
+  comb.hy = fmax2(a1.hy, a2.hy);
+  moveProxy(e, bi, comb, b.p - xf1.p);
+}
+
 HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h, int velIters, int posIters) {
   (void)cfg;
   e.b[0].island = e.b[1].island = e.b[2].island = false;
   uint32_t inIsland = 0;  // contacts
+  int ic[MAX_MANIFOLDS];          // island contacts in solver order
+  unsigned char icIsl[MAX_MANIFOLDS];
+  int nic = 0;
+  uint32_t islBodies[3];
+  int nIsl = 0;
   for (int seed = 2; seed >= 0; --seed) {
     if (e.b[seed].island) continue;
     if (!e.b[seed].awake) continue;
-    int ic[MAX_MANIFOLDS];
-    int nic = 0;
     uint32_t bm = 0;
     int stack[3];
     int sp = 0;
@@ -751,6 +781,7 @@ HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, E
       bm |= 1u << bi;
       setAwake(e.b[bi], true);
       uint32_t mine = bi == 0 ? HK_PAIRS_R1 : (bi == 1 ? HK_PAIRS_R2 : HK_PAIRS_PUCK);
+      if (!(mine & e.touch & e.enabled & ~HK_PAIRS_SENSOR & ~inIsland)) continue;
       for (int i = 0; i < e.ncontacts; ++i) {
         int pid = clistGet(e.clist, i);
         uint32_t bit = 1u << pid;
@@ -758,7 +789,13 @@ HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, E
         if (inIsland & bit) continue;
         if (!(e.enabled & bit) || !(e.touch & bit)) continue;
         if (HK_PAIRS_SENSOR & bit) continue;
-        if (nic < MAX_MANIFOLDS) ic[nic++] = pid; else e.nOverflow++;
+        if (nic < MAX_MANIFOLDS) {
+          ic[nic] = pid;
+          icIsl[nic] = (unsigned char)nIsl;
+          ++nic;
+        } else {
+          e.nOverflow++;
+        }
         inIsland |= bit;
         int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
         int other = (bA == bi) ? bB : bA;
@@ -768,57 +805,62 @@ HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, E
         e.b[other].island = true;
       }
     }
-    // ---- b2Island::Solve ----
-    for (int bi = 0; bi < 3; ++bi) {
-      if (!((bm >> bi) & 1u)) continue;
-      Body& b = e.b[bi];
-      b.c0 = b.c;
-      b.a0 = b.a;
-      b.v += h * (1.0f * mk(0.0f, 0.0f) + S.invMass[bi] * b.f);
-      b.w += h * S.invI[bi] * b.tq;
-      b.v *= fclamp(1.0f - h * b.ldamp, 0.0f, 1.0f);
-      b.w *= fclamp(1.0f - h * b.adamp, 0.0f, 1.0f);
-    }
-    VC vcs[MAX_MANIFOLDS];
-    int nvc = 0;
-    for (int k = 0; k < nic; ++k) {
-      int pid = ic[k];
-      int slot = findSlot(e, pid);
-      if (slot < 0) {
-        // touching contact whose Collide update was skipped (both bodies were asleep): geometry from the
-        // current poses, ids/impulses from the cache
-        if (e.nmf >= MAX_MANIFOLDS) {
-          e.nOverflow++;
-          continue;
-        }
-        slot = e.nmf++;
-        e.mfPid[slot] = pid;
-        evaluateManifold(S, e, pid, &e.mf[slot]);
-        int oldCount = getCount(e, pid);
-        for (int i = 0; i < e.mf[slot].count; ++i) {
-          e.mf[slot].ni[i] = 0.0f;
-          e.mf[slot].ti[i] = 0.0f;
-          for (int j = 0; j < oldCount; ++j)
-            if (cache.at(pid, j) == e.mf[slot].key[i]) {
-              e.mf[slot].ni[i] = u2f(cache.at(pid, 2 + 2 * j));
-              e.mf[slot].ti[i] = u2f(cache.at(pid, 3 + 2 * j));
-              break;
-            }
-        }
+    islBodies[nIsl++] = bm;
+  }
+  // ---- integrate velocities (b2Island::Solve, first loop) ----
+  Rot q0[3];
+  for (int bi = 0; bi < 3; ++bi) {
+    Body& b = e.b[bi];
+    q0[bi] = b.q;
+    if (!b.island) continue;
+    b.c0 = b.c;
+    b.a0 = b.a;
+    b.v += h * (1.0f * mk(0.0f, 0.0f) + S.invMass[bi] * b.f);
+    b.w += h * S.invI[bi] * b.tq;
+    b.v *= fclamp(1.0f - h * b.ldamp, 0.0f, 1.0f);
+    b.w *= fclamp(1.0f - h * b.adamp, 0.0f, 1.0f);
+  }
+  // ---- constraints ----
+  VC vcs[MAX_MANIFOLDS];
+  int nvc = 0;
+  for (int k = 0; k < nic; ++k) {
+    int pid = ic[k];
+    int slot = findSlot(e, pid);
+    if (slot < 0) {
+      // touching contact whose Collide update was skipped (both bodies were asleep): geometry from the
+      // current poses, ids/impulses from the cache
+      if (e.nmf >= MAX_MANIFOLDS) {
+        e.nOverflow++;
+        continue;
       }
-      if (e.mf[slot].count == 0) continue;
-      ic[nvc] = pid;
-      initConstraint(S, e, pid, slot, true, &vcs[nvc]);
-      ++nvc;
+      slot = e.nmf++;
+      e.mfPid[slot] = pid;
+      evaluateManifold(S, e, pid, &e.mf[slot]);
+      int oldCount = getCount(e, pid);
+      for (int i = 0; i < e.mf[slot].count; ++i) {
+        e.mf[slot].ni[i] = 0.0f;
+        e.mf[slot].ti[i] = 0.0f;
+        for (int j = 0; j < oldCount; ++j)
+          if (cache.at(pid, j) == e.mf[slot].key[i]) {
+            e.mf[slot].ni[i] = u2f(cache.at(pid, 2 + 2 * j));
+            e.mf[slot].ti[i] = u2f(cache.at(pid, 3 + 2 * j));
+            break;
+          }
+      }
     }
+    if (e.mf[slot].count == 0) continue;
+    ic[nvc] = pid;
+    icIsl[nvc] = icIsl[k];
+    initConstraint(S, e, pid, slot, true, &vcs[nvc]);
+    ++nvc;
+  }
+  if (nvc > 0) {
     for (int k = 0; k < nvc; ++k) warmStartConstraint(e, vcs[k]);
-    if (nvc > 0) {
-      for (int it = 0; it < velIters; ++it) {
-        bool changed = false;
-        for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
-        e.nVelIters++;
-        if (!changed) break;  // fixed point: all remaining sweeps are bit-identical no-ops
-      }
+    for (int it = 0; it < velIters; ++it) {
+      bool changed = false;
+      for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
+      e.nVelIters++;
+      if (!changed) break;  // fixed point: all remaining sweeps are bit-identical no-ops
     }
     // StoreImpulses
     for (int k = 0; k < nvc; ++k) {
@@ -830,45 +872,59 @@ HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, E
         cache.at(ic[k], 3 + 2 * j) = f2u(m.ti[j]);
       }
     }
-    for (int bi = 0; bi < 3; ++bi)
-      if ((bm >> bi) & 1u) integratePosition(e.b[bi], h);
-    bool positionSolved = false;
-    for (int it = 0; it < posIters; ++it) {
-      float minSeparation = 0.0f;
+  }
+  for (int bi = 0; bi < 3; ++bi)
+    if (e.b[bi].island) integratePosition(e.b[bi], h);
+  // ---- position iterations, each island stops on its own criterion ----
+  uint32_t islSolved = 0;  // positionSolved per island
+  {
+    uint32_t withContacts = 0;
+    for (int k = 0; k < nvc; ++k) withContacts |= 1u << icIsl[k];
+    islSolved = ~withContacts;  // an island without contacts is solved by the first (empty) iteration
+    uint32_t active = withContacts;
+    for (int it = 0; it < posIters && active; ++it) {
+      float minSep[3] = {0.0f, 0.0f, 0.0f};
       for (int k = 0; k < nvc; ++k) {
+        int isl = icIsl[k];
+        if (!((active >> isl) & 1u)) continue;
         const Manifold& m = e.mf[vcs[k].slot];
-        minSeparation = fmin2(minSeparation, solvePositionConstraint(S, e, ic[k], m, m.count, false));
+        minSep[isl] = fmin2(minSep[isl], solvePositionConstraint(S, e, ic[k], m, m.count, false));
       }
-      if (minSeparation >= -3.0f * HK_LINEAR_SLOP) {
-        positionSolved = true;
-        break;
-      }
-    }
-    for (int bi = 0; bi < 3; ++bi)
-      if ((bm >> bi) & 1u) syncTransform(S, e.b[bi], bi);
-    {
-      float minSleepTime = HK_MAXFLOAT;
-      const float linTolSqr = HK_LINEAR_SLEEP_TOL * HK_LINEAR_SLEEP_TOL;
-      const float angTolSqr = HK_ANGULAR_SLEEP_TOL * HK_ANGULAR_SLEEP_TOL;
-      for (int bi = 0; bi < 3; ++bi) {
-        if (!((bm >> bi) & 1u)) continue;
-        Body& b = e.b[bi];
-        if (b.w * b.w > angTolSqr || dot(b.v, b.v) > linTolSqr) {
-          b.sleep = 0.0f;
-          minSleepTime = 0.0f;
-        } else {
-          b.sleep += h;
-          minSleepTime = fmin2(minSleepTime, b.sleep);
+      for (int isl = 0; isl < nIsl; ++isl) {
+        if (!((active >> isl) & 1u)) continue;
+        if (minSep[isl] >= -3.0f * HK_LINEAR_SLOP) {
+          active &= ~(1u << isl);
+          islSolved |= 1u << isl;
         }
-      }
-      if (minSleepTime >= HK_TIME_TO_SLEEP && positionSolved) {
-        for (int bi = 0; bi < 3; ++bi)
-          if ((bm >> bi) & 1u) setAwake(e.b[bi], false);
       }
     }
   }
+  for (int bi = 0; bi < 3; ++bi)
+    if (e.b[bi].island) syncTransform(S, e.b[bi], bi);
+  // ---- sleep management per island ----
+  for (int isl = 0; isl < nIsl; ++isl) {
+    const uint32_t bm = islBodies[isl];
+    float minSleepTime = HK_MAXFLOAT;
+    const float linTolSqr = HK_LINEAR_SLEEP_TOL * HK_LINEAR_SLEEP_TOL;
+    const float angTolSqr = HK_ANGULAR_SLEEP_TOL * HK_ANGULAR_SLEEP_TOL;
+    for (int bi = 0; bi < 3; ++bi) {
+      if (!((bm >> bi) & 1u)) continue;
+      Body& b = e.b[bi];
+      if (b.w * b.w > angTolSqr || dot(b.v, b.v) > linTolSqr) {
+        b.sleep = 0.0f;
+        minSleepTime = 0.0f;
+      } else {
+        b.sleep += h;
+        minSleepTime = fmin2(minSleepTime, b.sleep);
+      }
+    }
+    if (minSleepTime >= HK_TIME_TO_SLEEP && ((islSolved >> isl) & 1u)) {
+      for (int bi = 0; bi < 3; ++bi)
+        if ((bm >> bi) & 1u) setAwake(e.b[bi], false);
+    }
+  }
   for (int bi = 2; bi >= 0; --bi)
-    if (e.b[bi].island) synchronizeFixtures(S, e, bi);
+    if (e.b[bi].island) synchronizeFixturesQ0(S, e, bi, q0[bi]);
   findNewContacts(S, e);
 }
 
@@ -881,6 +937,7 @@ HK_HD Sweep bodySweep(const Scene& S, const Body& b, int bi) {
   s.a0 = b.a0;
   s.a = b.a;
   s.alpha0 = b.alpha0;
+  s.rot = bi != B_PUCK;
   return s;
 }
 HK_HD void bodyAdvance(const Scene& S, Body& b, int bi, float alpha) {  // b2Body::Advance
@@ -891,7 +948,7 @@ HK_HD void bodyAdvance(const Scene& S, Body& b, int bi, float alpha) {  // b2Bod
   b.alpha0 = s.alpha0;
   b.c = b.c0;
   b.a = b.a0;
-  b.q = rotOf(b.a);
+  b.q = rotForBody(bi, b.a);
   b.p = b.c - mul(b.q, s.lc);
 }
 
@@ -952,6 +1009,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
         sA.c0 = sA.c = mk(S.spx[fA], S.spy[fA]);
         sA.a0 = sA.a = 0.0f;
         sA.alpha0 = salpha[sb];
+        sA.rot = false;
         Sweep sB = bodySweep(S, B, bi);
         int state;
         float t;

@@ -6,6 +6,8 @@
 // and is never a fallback: the package fails loudly without the CUDA library.
 #include <cstring>
 #include <vector>
+#define HK_FAST_DEBUG 1
+namespace hk { long long g_fast_bail[16]; }
 #include "../../include/hockey_b200.h"
 #include "../../hockey_env_b200/csrc/hk_tick.cuh"
 
@@ -18,6 +20,8 @@ struct HostBatch {
   std::vector<Env> envs;
   std::vector<uint32_t> cache;  // [27*6][n]
   double stats[HK_STATS_DIM];
+  int use_fast = 0;
+  long long nFast = 0, nSlow = 0;
   Cache cacheOf(int64_t i) { Cache c; c.base = cache.data() + i; c.stride = (size_t)n; return c; }
 };
 
@@ -60,11 +64,20 @@ void hs_step(void* h, const float* action, int stride, int pol1, int pol2, int f
     Env e;
     groupsToEnv(g, e);
     TickStats st; tickStatsZero(st);
-    envTick(b->S, b->cfg, b->cacheOf(i), e, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st);
+    bool done_fast = false;
+    if (b->use_fast) {
+      Env w = e;
+      TickStats st2; tickStatsZero(st2);
+      if (envTickFast(b->S, b->cfg, w, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st2)) { e = w; st = st2; done_fast = true; }
+    }
+    if (done_fast) b->nFast++; else { b->nSlow++; envTick(b->S, b->cfg, b->cacheOf(i), e, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st); }
     b->envs[i] = e;
     addStats(b->stats, st);
   }
 }
+void hs_bail_counts(long long* out) { for (int i = 0; i < 16; ++i) out[i] = hk::g_fast_bail[i]; }
+void hs_set_fast(void* h, int on) { ((HostBatch*)h)->use_fast = on; }
+void hs_fast_counts(void* h, long long* out) { out[0] = ((HostBatch*)h)->nFast; out[1] = ((HostBatch*)h)->nSlow; }
 void hs_get_obs(void* h, float* obs, float* obs2) {
   HostBatch* b = (HostBatch*)h;
   for (int64_t i = 0; i < b->n; ++i) { if (obs) getObs(b->envs[i], obs + 18 * i); if (obs2) getObs2(b->envs[i], obs2 + 18 * i); }

@@ -47,6 +47,8 @@ def lib():
         L.hs_clear_stats.argtypes = [vp]
         L.hs_scene.argtypes = [vp, vp, i64]
         L.hs_scene_size.restype = i64
+        L.hs_set_fast.argtypes = [vp, i32]
+        L.hs_fast_counts.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -55,10 +57,11 @@ _p = O._p
 
 
 class HostSimBatch:
-    def __init__(self, n, mode=0, keep_mode=True, seed=0, env_id_offset=0):
+    def __init__(self, n, mode=0, keep_mode=True, seed=0, env_id_offset=0, fast=False):
         self.n = int(n)
         self.L = lib()
         self.h = self.L.hs_create(self.n, int(mode), int(bool(keep_mode)), int(seed), int(env_id_offset))
+        self.L.hs_set_fast(self.h, int(bool(fast)))
 
     def __del__(self):
         try:
@@ -107,6 +110,11 @@ class HostSimBatch:
     def set_obs_state(self, obs18):
         s = np.ascontiguousarray(obs18, np.float32)
         self.L.hs_set_obs_state(self.h, _p(s))
+
+    def fast_counts(self):
+        c = np.zeros(2, np.int64)
+        self.L.hs_fast_counts(self.h, _p(c))
+        return int(c[0]), int(c[1])
 
     def stats(self):
         s = np.zeros(16, np.float64)

@@ -347,6 +347,7 @@ HK_HD void envStep(const Scene& S, const Config& cfg, const Cache& cache, Env& e
     }
   }
   worldStep(S, cfg, cache, e, (float)(1.0 / HK_FPS), 6 * 30, 2 * 30);
+  if (e.aborted) return;
   if (e.time >= cfg.max_timesteps) e.done = true;
   e.time += 1;
   ++e.tick;

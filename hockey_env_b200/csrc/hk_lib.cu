@@ -108,8 +108,8 @@ struct KParams {
   float4* core;
   uint32_t* cache;
   double* stats;
-  int32_t* queue;    // env indices that need the general path this tick
-  uint32_t* qctl;    // [0] queue length, [1] slow-kernel blocks finished
+  int32_t* queue;    // [2][n] env indices queued for tier 1 (k_mid) and tier 2 (k_long) this tick
+  uint32_t* qctl;    // [0],[1]: tier-1 queue length / finished blocks; [2],[3]: tier-2
   int64_t n;
   int64_t env_id_offset;
   Config cfg;
@@ -162,11 +162,11 @@ __global__ void __launch_bounds__(kBlock) k_step(KParams P, StepIO io) {
   flushStats(P.stats, st);
 }
 
-// ---- the per-tick pipeline: k_fast over all envs, then k_slow over the queue k_fast produced ----------------
-// k_fast proves "nothing to solve" per env (hk_fast.cuh) and finishes those ticks with a small register
-// footprint; every other env index is appended to the queue (one atomic per warp).  k_slow runs the general
-// path on the compacted queue, so lanes that iterate the contact solver sit next to each other instead of
-// idling 30 neighbours (ncu, round 1: 1.6 active lanes per solver instruction before the split).
+// ---- the per-tick pipeline: k_fast over all envs, then the general path over the queues (three-tier cascade) ----------------
+// k_fast (tier 0) proves "nothing to solve" per env (hk_fast.cuh) and finishes those ticks with a small register
+// footprint; every other env index is appended to the tier-1 queue (one atomic per warp).  The general path
+// then runs on compacted queues, so lanes that iterate the contact solver sit next to each other instead of
+// idling 30 neighbours (ncu, round 1: 1.6 active lanes per solver instruction in the monolithic kernel).
 __global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
   __shared__ Scene S;
   stageScene(&S);
@@ -194,32 +194,61 @@ __global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
   flushStats(P.stats, st);
 }
 
-__global__ void __launch_bounds__(kSlowBlock) k_slow(KParams P, StepIO io) {
+// Tier 2 and 3 of the cascade run the same general path (hk::envTick) over a compacted queue:
+//   TIER == 1 (k_mid): budgeted -- a velocity solve must converge (fixed point / short cycle) within kMidSweeps
+//                      sweeps and no continuous-collision EVENT may occur; otherwise the env is appended to the
+//                      next queue with nothing committed;
+//   TIER == 2 (k_long): unlimited.  Its lanes are the rare long solves and TOI events, packed densely, instead
+//                      of each of them stalling 31 converged neighbours for up to 180 sweeps.
+constexpr int kMidSweeps = 24;
+template <int TIER>
+__global__ void __launch_bounds__(kSlowBlock) k_general(KParams P, StepIO io) {
   __shared__ Scene S;
   stageScene(&S);
-  const unsigned count = *((volatile uint32_t*)&P.qctl[0]);
+  uint32_t* ctl = P.qctl + 2 * (TIER - 1);          // [0] length of my queue, [1] my finished blocks
+  const int32_t* myQueue = P.queue + (TIER - 1) * P.n;
+  const unsigned count = *((volatile uint32_t*)&ctl[0]);
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   TickStats st;
   tickStatsZero(st);
+  bool need = false;
+  int64_t i = 0;
   if (j < (int64_t)count) {
-    const int64_t i = P.queue[j];
+    i = myQueue[j];
     Env e;
     loadEnv(P.core, P.n, i, e);
     Cache cache;
     cache.base = P.cache + i;
     cache.stride = (size_t)P.n;
-    envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st);
-    storeEnv(P.core, P.n, i, e);
+    const bool ok = envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st,
+                            TIER == 1 ? kMidSweeps : (1 << 20), TIER != 1);
+    if (ok) storeEnv(P.core, P.n, i, e);
+    else {
+      tickStatsZero(st);
+      need = true;
+    }
   }
-  if ((int64_t)blockIdx.x * blockDim.x < (int64_t)count) flushStats(P.stats, st);
-  // the last block to finish re-arms the queue for the next tick
+  if ((int64_t)blockIdx.x * blockDim.x < (int64_t)count) {
+    if (TIER == 1) {
+      const unsigned m = __ballot_sync(0xffffffffu, need);
+      if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&P.qctl[2], (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need) P.queue[P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+      }
+    }
+    flushStats(P.stats, st);
+  }
+  // the last block to finish re-arms this tier's queue for the next tick
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    unsigned t = atomicAdd(&P.qctl[1], 1u);
+    unsigned t = atomicAdd(&ctl[1], 1u);
     if (t == gridDim.x - 1) {
-      P.qctl[0] = 0;
-      P.qctl[1] = 0;
+      ctl[0] = 0;
+      ctl[1] = 0;
       __threadfence();
     }
   }
@@ -382,9 +411,9 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->cache, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->stats, sizeof(double) * HK_STATS_DIM);
-  if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * (size_t)n_envs);
-  if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 2);
-  if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 2);
+  if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * 2 * (size_t)n_envs);
+  if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 4);
+  if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 4);
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
   if (err == cudaSuccess) {
@@ -458,7 +487,8 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
     k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
   } else {
     k_fast<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
-    k_slow<<<h->gridSlow(), kSlowBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+    k_general<1><<<h->gridSlow(), kSlowBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+    k_general<2><<<h->gridSlow(), kSlowBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
   }
   HK_CUDA(cudaGetLastError());
   return HK_OK;

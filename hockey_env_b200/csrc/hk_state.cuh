@@ -121,6 +121,9 @@ HK_HD void groupsToEnv(const F4* g, Env& e) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   e.nVelIters = e.nToiEvents = e.nOverflow = 0;
+  e.sweepBudget = 1 << 20;
+  e.allowToiEvents = true;
+  e.aborted = false;
 }
 
 // ---- canonical record <-> Env ------------------------------------------------------------------
@@ -266,6 +269,9 @@ HK_HD void unpackRecord(const uint32_t* r, Env& e, const Cache& cache) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   e.nVelIters = e.nToiEvents = e.nOverflow = 0;
+  e.sweepBudget = 1 << 20;
+  e.allowToiEvents = true;
+  e.aborted = false;
 }
 
 // HockeyEnv.set_state (hockey_env.py:594-608): 18 visible values; goes through b2Body::SetTransform

@@ -103,14 +103,20 @@ HK_HD void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64_t env_id
   }
 }
 
-// general tick
-HK_HD void envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e, uint64_t env_id, size_t i,
-                   const StepIO& io, bool write, TickStats& st) {
+// general tick.  sweepBudget / allowToiEvents are the budgets of the calling tier (unlimited: 1<<20, true);
+// returns false -- with nothing committed -- if a budget ran out (the next tier redoes the tick from the stored state)
+HK_HD bool envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e, uint64_t env_id, size_t i,
+                   const StepIO& io, bool write, TickStats& st, int sweepBudget = 1 << 20, bool allowToiEvents = true) {
   float a[8];
   policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
   const int had1 = e.has1, had2 = e.has2;
+  e.sweepBudget = sweepBudget;
+  e.allowToiEvents = allowToiEvents;
+  e.aborted = false;
   envStep(S, cfg, cache, e, a);
+  if (e.aborted) return false;
   tickFinish(S, cfg, e, env_id, i, io, write, st, had1, had2);
+  return true;
 }
 
 // fast tick: returns false (e unusable, nothing written) if the env needs the general path this tick
@@ -132,6 +138,9 @@ HK_HD void envCreate(const Scene& S, const Config& cfg, Env& e, uint64_t env_id)
   e.episode = 0;
   e.tick = 0;
   e.nVelIters = e.nToiEvents = e.nOverflow = 0;
+  e.sweepBudget = 1 << 20;
+  e.allowToiEvents = true;
+  e.aborted = false;
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   U4 r = philox(cfg.seed, env_id, 0, HK_STREAM_PHASE0);

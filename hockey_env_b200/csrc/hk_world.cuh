@@ -18,6 +18,17 @@
 
 namespace hk {
 
+#if defined(HK_FAST_DEBUG) && !defined(__CUDA_ARCH__)
+extern long long g_iter_hist[2][182];
+extern long long g_nvc_hist[16];
+extern long long g_period_hist[16];
+#define HK_ITER_HIST(w, n) g_iter_hist[w][n]++
+#define HK_NVC_HIST(n) g_nvc_hist[n]++
+#else
+#define HK_ITER_HIST(w, n)
+#define HK_NVC_HIST(n)
+#endif
+
 enum { MAX_MANIFOLDS = 8, MAX_CLIST = 12 };
 
 struct Body {
@@ -78,6 +89,11 @@ struct Env {
   int nmf;
   // counters (statistics)
   uint32_t nVelIters, nToiEvents, nOverflow;
+  // budgets of this tier (hk_lib.cu cascade); exceeding one sets `aborted` and the tick is redone, from the
+  // stored state, by the next tier.  Nothing is committed before the end of a tick, so aborting is free.
+  int sweepBudget;   // max velocity sweeps a solve may need to converge (>= 180: unlimited)
+  bool allowToiEvents;
+  bool aborted;
 };
 
 struct Config {
@@ -298,7 +314,9 @@ HK_HD void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) 
   }
 }
 
-// b2Contact::Update
+// b2Contact::Update.  Manifold ids and warm-start impulses of the contacts handled this tick live in the
+// manifold slots; the global cache is read the first time a pair is updated in a tick and written once, by
+// commitCache(), when the tick completes.
 HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, Env& e, int pid) {
   const uint32_t bit = 1u << pid;
   e.enabled |= bit;
@@ -312,13 +330,23 @@ HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, 
     Manifold tmp;
     evaluateManifold(S, e, pid, &tmp);
     touching = tmp.count > 0;
-    int oldCount = getCount(e, pid);
+    int oldCount;
     uint32_t oldKey[2] = {0, 0};
     float oldNi[2] = {0, 0}, oldTi[2] = {0, 0};
-    for (int j = 0; j < oldCount; ++j) {
-      oldKey[j] = cache.at(pid, j);
-      oldNi[j] = u2f(cache.at(pid, 2 + 2 * j));
-      oldTi[j] = u2f(cache.at(pid, 3 + 2 * j));
+    if (slot >= 0) {
+      oldCount = e.mf[slot].count;
+      for (int j = 0; j < oldCount; ++j) {
+        oldKey[j] = e.mf[slot].key[j];
+        oldNi[j] = e.mf[slot].ni[j];
+        oldTi[j] = e.mf[slot].ti[j];
+      }
+    } else {
+      oldCount = getCount(e, pid);
+      for (int j = 0; j < oldCount; ++j) {
+        oldKey[j] = cache.at(pid, j);
+        oldNi[j] = u2f(cache.at(pid, 2 + 2 * j));
+        oldTi[j] = u2f(cache.at(pid, 3 + 2 * j));
+      }
     }
     for (int i = 0; i < tmp.count; ++i) {
       tmp.ni[i] = 0.0f;
@@ -330,11 +358,6 @@ HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, 
           break;
         }
       }
-    }
-    for (int i = 0; i < tmp.count; ++i) {
-      cache.at(pid, i) = tmp.key[i];
-      cache.at(pid, 2 + 2 * i) = f2u(tmp.ni[i]);
-      cache.at(pid, 3 + 2 * i) = f2u(tmp.ti[i]);
     }
     setCount(e, pid, tmp.count);
     if (touching) {
@@ -359,6 +382,21 @@ HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, 
   }
   if (touching) e.touch |= bit; else e.touch &= ~bit;
   if (!wasTouching && touching) beginContact(cfg, e, pid);
+}
+
+// write the ids / impulses of every manifold handled this tick to the persistent cache (end of a completed tick)
+HK_HD void commitCache(const Cache& cache, const Env& e) {
+  for (int sIdx = 0; sIdx < e.nmf; ++sIdx) {
+    const Manifold& m = e.mf[sIdx];
+    const int pid = e.mfPid[sIdx];
+    if (!((e.exist >> pid) & 1u)) continue;
+    if (getCount(e, pid) != m.count) continue;  // pair was destroyed and re-created within the tick
+    for (int j = 0; j < m.count; ++j) {
+      cache.at(pid, j) = m.key[j];
+      cache.at(pid, 2 + 2 * j) = f2u(m.ni[j]);
+      cache.at(pid, 3 + 2 * j) = f2u(m.ti[j]);
+    }
+  }
 }
 
 // b2ContactManager::Collide
@@ -663,6 +701,92 @@ HK_HD bool solveVelocityConstraint(Env& e, VC& vc) {
   return changed;
 }
 
+// ---- the 180 velocity iterations, cut short exactly ----------------------------------------------------
+// One sweep is a deterministic map F of the solver state s = (body velocities, accumulated impulses).
+//  * s_k == s_(k-1) (no non-zero impulse increment in sweep k): fixed point, every later sweep is a no-op;
+//  * s_k == s_(k-2): the sequence has entered a period-2 cycle (observed in ~20 % of solves: the last bit of
+//    an impulse and of a velocity flip back and forth) -- the state after all N sweeps is s_k or s_(k-1)
+//    depending on the parity of N - k.
+// Either way the result is numerically identical to running all N sweeps, which is what the oracle does.
+struct SolveSnap {
+  float v[9];
+  float imp[MAX_MANIFOLDS * 4];
+};
+HK_HD void snapSave(const Env& e, const VC* vcs, int nvc, SolveSnap& s) {
+  for (int b = 0; b < 3; ++b) {
+    s.v[3 * b] = e.b[b].v.x;
+    s.v[3 * b + 1] = e.b[b].v.y;
+    s.v[3 * b + 2] = e.b[b].w;
+  }
+  for (int k = 0; k < nvc; ++k) {
+    s.imp[4 * k] = vcs[k].pt[0].ni;
+    s.imp[4 * k + 1] = vcs[k].pt[0].ti;
+    s.imp[4 * k + 2] = vcs[k].count > 1 ? vcs[k].pt[1].ni : 0.0f;
+    s.imp[4 * k + 3] = vcs[k].count > 1 ? vcs[k].pt[1].ti : 0.0f;
+  }
+}
+HK_HD bool snapEqual(const SolveSnap& a, const SolveSnap& b, int nvc) {
+  bool eq = true;
+  for (int i = 0; i < 9; ++i) eq = eq && (a.v[i] == b.v[i]);
+  for (int i = 0; i < 4 * nvc; ++i) eq = eq && (a.imp[i] == b.imp[i]);
+  return eq;
+}
+HK_HD void snapRestore(Env& e, VC* vcs, int nvc, const SolveSnap& s) {
+  for (int b = 0; b < 3; ++b) {
+    e.b[b].v = mk(s.v[3 * b], s.v[3 * b + 1]);
+    e.b[b].w = s.v[3 * b + 2];
+  }
+  for (int k = 0; k < nvc; ++k) {
+    vcs[k].pt[0].ni = s.imp[4 * k];
+    vcs[k].pt[0].ti = s.imp[4 * k + 1];
+    if (vcs[k].count > 1) {
+      vcs[k].pt[1].ni = s.imp[4 * k + 2];
+      vcs[k].pt[1].ti = s.imp[4 * k + 3];
+    }
+  }
+}
+#define HK_CYCLE_RING 8
+// returns the number of sweeps executed, or -1 if the tier's sweep budget ran out before the state repeated
+HK_HD int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
+  SolveSnap ring[HK_CYCLE_RING];  // ring[(sweep index) % RING] = state after that sweep
+  const int kFirstSnap = 3;
+  int it = 0;
+  for (; it < velIters; ++it) {
+    bool changed = false;
+    for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
+    e.nVelIters++;
+    if (!changed) {
+      ++it;
+      break;
+    }
+    if (it >= kFirstSnap) {
+      SolveSnap cur;
+      snapSave(e, vcs, nvc, cur);
+      int period = 0;
+      for (int p = 2; p <= HK_CYCLE_RING && it - p >= kFirstSnap; ++p) {
+        if (snapEqual(cur, ring[(it - p) % HK_CYCLE_RING], nvc)) {
+          period = p;
+          break;
+        }
+      }
+      if (period) {
+        // state after sweep j (j >= it - period) equals the stored state of sweep it - period + ((j - it) mod period)
+        const int remaining = velIters - 1 - it;
+        const int r = remaining % period;
+        if (r) snapRestore(e, vcs, nvc, ring[(it - period + r) % HK_CYCLE_RING]);
+#if defined(HK_FAST_DEBUG) && !defined(__CUDA_ARCH__)
+        g_period_hist[period]++;
+#endif
+        ++it;
+        break;
+      }
+      ring[it % HK_CYCLE_RING] = cur;
+    }
+    if (it + 1 >= e.sweepBudget && it + 1 < velIters) return -1;
+  }
+  return it;
+}
+
 // b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints for one contact.
 // In a TOI island every contact is (static A, the TOI dynamic body B), so the TOI mass rule
 // ("only the two TOI bodies have mass") reduces to the normal masses.
@@ -856,20 +980,19 @@ HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, E
   }
   if (nvc > 0) {
     for (int k = 0; k < nvc; ++k) warmStartConstraint(e, vcs[k]);
-    for (int it = 0; it < velIters; ++it) {
-      bool changed = false;
-      for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
-      e.nVelIters++;
-      if (!changed) break;  // fixed point: all remaining sweeps are bit-identical no-ops
+    int itc = runVelocityIterations(e, vcs, nvc, velIters);
+    if (itc < 0) {
+      e.aborted = true;
+      return;
     }
+    HK_ITER_HIST(0, itc);
+    HK_NVC_HIST(nvc);
     // StoreImpulses
     for (int k = 0; k < nvc; ++k) {
       Manifold& m = e.mf[vcs[k].slot];
       for (int j = 0; j < vcs[k].count; ++j) {
         m.ni[j] = vcs[k].pt[j].ni;
         m.ti[j] = vcs[k].pt[j].ti;
-        cache.at(ic[k], 2 + 2 * j) = f2u(m.ni[j]);
-        cache.at(ic[k], 3 + 2 * j) = f2u(m.ti[j]);
       }
     }
   }
@@ -1026,6 +1149,10 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
       }
     }
     if (minPid < 0 || 1.0f - 10.0f * HK_EPS < minAlpha) break;
+    if (!e.allowToiEvents) {
+      e.aborted = true;
+      return;
+    }
     e.nToiEvents++;
 
     const int fA = S.pairFA[minPid], fB = S.pairFB[minPid];
@@ -1099,12 +1226,12 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
       initConstraint(S, e, ic[k], slot, false, &vcs[nvc]);
       ++nvc;
     }
-    for (int it = 0; it < velIters; ++it) {
-      bool changed = false;
-      for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
-      e.nVelIters++;
-      if (!changed) break;
+    int itc = runVelocityIterations(e, vcs, nvc, velIters);
+    if (itc < 0) {
+      e.aborted = true;
+      return;
     }
+    HK_ITER_HIST(1, itc);
     integratePosition(B, subDt);
     syncTransform(S, B, bi);
     B.island = false;
@@ -1124,7 +1251,10 @@ HK_HD void worldStep(const Scene& S, const Config& cfg, const Cache& cache, Env&
   }
   collide(S, cfg, cache, e);
   solveIslands(S, cfg, cache, e, dt, velIters, posIters);
+  if (e.aborted) return;
   if (e.exist & HK_PAIRS_TOI) solveTOI(S, cfg, cache, e, dt, velIters);
+  if (e.aborted) return;
+  commitCache(cache, e);
   for (int bi = 0; bi < 3; ++bi) {  // ClearForces
     e.b[bi].f = mk(0.0f, 0.0f);
     e.b[bi].tq = 0.0f;

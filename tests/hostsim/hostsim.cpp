@@ -4,10 +4,11 @@
 // non-GPU test tier can diff the kernel's per-env arithmetic against the CPU oracle bit-for-bit
 // (there is no GPU in the build container).  It is not reachable from the hockey_env_b200 package
 // and is never a fallback: the package fails loudly without the CUDA library.
+#include <cstdio>
 #include <cstring>
 #include <vector>
 #define HK_FAST_DEBUG 1
-namespace hk { long long g_fast_bail[16]; }
+namespace hk { long long g_fast_bail[16]; long long g_iter_hist[2][182]; long long g_nvc_hist[16]; long long g_period_hist[16]; int g_dbg_left = 5; }
 #include "../../include/hockey_b200.h"
 #include "../../hockey_env_b200/csrc/hk_tick.cuh"
 
@@ -21,7 +22,8 @@ struct HostBatch {
   std::vector<uint32_t> cache;  // [27*6][n]
   double stats[HK_STATS_DIM];
   int use_fast = 0;
-  long long nFast = 0, nSlow = 0;
+  long long nFast = 0, nSlow = 0, nLong = 0;
+  int mid_budget = 24;
   Cache cacheOf(int64_t i) { Cache c; c.base = cache.data() + i; c.stride = (size_t)n; return c; }
 };
 
@@ -70,14 +72,23 @@ void hs_step(void* h, const float* action, int stride, int pol1, int pol2, int f
       TickStats st2; tickStatsZero(st2);
       if (envTickFast(b->S, b->cfg, w, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st2)) { e = w; st = st2; done_fast = true; }
     }
-    if (done_fast) b->nFast++; else { b->nSlow++; envTick(b->S, b->cfg, b->cacheOf(i), e, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st); }
+    if (done_fast) b->nFast++;
+    else if (b->use_fast) {
+      // the kernel cascade: budgeted middle tier, then the unlimited tier, each from the stored state
+      Env w = e;
+      TickStats st2; tickStatsZero(st2);
+      if (envTick(b->S, b->cfg, b->cacheOf(i), w, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st2, b->mid_budget, false)) { e = w; st = st2; b->nSlow++; }
+      else { b->nLong++; envTick(b->S, b->cfg, b->cacheOf(i), e, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st); }
+    } else { b->nSlow++; envTick(b->S, b->cfg, b->cacheOf(i), e, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st); }
     b->envs[i] = e;
     addStats(b->stats, st);
   }
 }
 void hs_bail_counts(long long* out) { for (int i = 0; i < 16; ++i) out[i] = hk::g_fast_bail[i]; }
+void hs_iter_hist(long long* out) { for (int w = 0; w < 2; ++w) for (int i = 0; i < 182; ++i) out[w * 182 + i] = hk::g_iter_hist[w][i]; for (int i = 0; i < 16; ++i) out[364 + i] = hk::g_period_hist[i]; }
 void hs_set_fast(void* h, int on) { ((HostBatch*)h)->use_fast = on; }
-void hs_fast_counts(void* h, long long* out) { out[0] = ((HostBatch*)h)->nFast; out[1] = ((HostBatch*)h)->nSlow; }
+void hs_fast_counts(void* h, long long* out) { out[0] = ((HostBatch*)h)->nFast; out[1] = ((HostBatch*)h)->nSlow; out[2] = ((HostBatch*)h)->nLong; }
+void hs_set_mid_budget(void* h, int b) { ((HostBatch*)h)->mid_budget = b; }
 void hs_get_obs(void* h, float* obs, float* obs2) {
   HostBatch* b = (HostBatch*)h;
   for (int64_t i = 0; i < b->n; ++i) { if (obs) getObs(b->envs[i], obs + 18 * i); if (obs2) getObs2(b->envs[i], obs2 + 18 * i); }

@@ -49,6 +49,7 @@ def lib():
         L.hs_scene_size.restype = i64
         L.hs_set_fast.argtypes = [vp, i32]
         L.hs_fast_counts.argtypes = [vp, vp]
+        L.hs_set_mid_budget.argtypes = [vp, i32]
         _lib = L
     return _lib
 
@@ -112,9 +113,9 @@ class HostSimBatch:
         self.L.hs_set_obs_state(self.h, _p(s))
 
     def fast_counts(self):
-        c = np.zeros(2, np.int64)
+        c = np.zeros(3, np.int64)
         self.L.hs_fast_counts(self.h, _p(c))
-        return int(c[0]), int(c[1])
+        return int(c[0]), int(c[1]), int(c[2])
 
     def stats(self):
         s = np.zeros(16, np.float64)

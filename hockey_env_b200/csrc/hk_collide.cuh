@@ -19,6 +19,7 @@ HK_HD uint32_t makeKey(int indexA, int indexB, int typeA, int typeB) {
 
 struct Manifold {
   int type, count;
+  float sepBound;  // lower bound of the core-shape distance at the evaluated poses (max face separation seen)
   V2 localNormal, localPoint;
   V2 lp[2];
   uint32_t key[2];
@@ -29,8 +30,9 @@ HK_HD V2 polyV(const Poly& p, int i) { return mk(p.vx[i], p.vy[i]); }
 HK_HD V2 polyN(const Poly& p, int i) { return mk(p.nx[i], p.ny[i]); }
 
 // ---- polygon (A) vs circle (B, centre at body origin) -------------------------------------------
-HK_HD void collidePolygonCircle(Manifold* m, const Poly& polyA, const Xf& xfA, V2 circleCenterWorld, float circleRadius) {
+HK_HD_NOINLINE void collidePolygonCircle(Manifold* m, const Poly& polyA, const Xf& xfA, V2 circleCenterWorld, float circleRadius) {
   m->count = 0;
+  m->sepBound = -HK_MAXFLOAT;
   V2 cLocal = mulT(xfA, circleCenterWorld);
   int normalIndex = 0;
   float separation = -HK_MAXFLOAT;
@@ -38,7 +40,10 @@ HK_HD void collidePolygonCircle(Manifold* m, const Poly& polyA, const Xf& xfA, V
   int vertexCount = polyA.count;
   for (int i = 0; i < vertexCount; ++i) {
     float s = dot(polyN(polyA, i), cLocal - polyV(polyA, i));
-    if (s > radius) return;
+    if (s > radius) {
+      m->sepBound = s;
+      return;
+    }
     if (s > separation) {
       separation = s;
       normalIndex = i;
@@ -47,6 +52,7 @@ HK_HD void collidePolygonCircle(Manifold* m, const Poly& polyA, const Xf& xfA, V
   int vertIndex1 = normalIndex;
   int vertIndex2 = vertIndex1 + 1 < vertexCount ? vertIndex1 + 1 : 0;
   V2 v1 = polyV(polyA, vertIndex1), v2 = polyV(polyA, vertIndex2);
+  m->sepBound = separation;
   m->type = MANIFOLD_FACE_A;
   m->lp[0] = mk(0.0f, 0.0f);
   m->key[0] = 0;
@@ -173,9 +179,11 @@ HK_HD_NOINLINE void collidePolygons(Manifold* m, const Poly& polyA, const Xf& xf
   const float totalRadius = HK_POLYGON_RADIUS + HK_POLYGON_RADIUS;
   int edgeA = 0;
   float separationA = findMaxSeparation(&edgeA, polyA, xfA, polyB, xfB);
+  m->sepBound = separationA;  // any face separation is a lower bound of the distance between the convex cores
   if (separationA > totalRadius) return;
   int edgeB = 0;
   float separationB = findMaxSeparation(&edgeB, polyB, xfB, polyA, xfA);
+  m->sepBound = fmax2(separationA, separationB);
   if (separationB > totalRadius) return;
   const float k_relativeTol = 0.98f;
   const float k_absoluteTol = 0.001f;
@@ -464,7 +472,7 @@ HK_HD_NOINLINE float gjkDistance(SimplexCache* cache, const Proxy& proxyA, const
 }
 
 // b2TestOverlap(shapeA, shapeB, xfA, xfB): sensor test of b2Contact::Update (goal polygon vs puck)
-HK_HD bool testOverlapPolyPuck(const Poly& poly, const Xf& xfA, V2 puckCenter, float puckRadius) {
+HK_HD_NOINLINE bool testOverlapPolyPuck(const Poly& poly, const Xf& xfA, V2 puckCenter, float puckRadius) {
   Proxy pa, pb;
   pa.poly = &poly;
   pa.radius = HK_POLYGON_RADIUS;
@@ -493,7 +501,7 @@ struct SepFn {
   V2 localPoint, axis;
 };
 
-HK_HD float sepFindMin(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int* indexA,
+HK_HD_NOINLINE float sepFindMin(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int* indexA,
                        int* indexB, float t) {
   Xf xfA, xfB;
   sweepXf(sA, &xfA, t);
@@ -525,7 +533,7 @@ HK_HD float sepFindMin(const SepFn& f, const Proxy& pA, const Sweep& sA, const P
   }
 }
 
-HK_HD float sepEvaluate(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int indexA,
+HK_HD_NOINLINE float sepEvaluate(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int indexA,
                         int indexB, float t) {
   Xf xfA, xfB;
   sweepXf(sA, &xfA, t);

@@ -22,12 +22,20 @@
 namespace hk {
 
 #define HK_FAST_EPS 0.005f
+// bail reason -> work class of the general tier (hk_lib.cu sorts the slow queue by class so that the lanes of a
+// warp do the same kind of work): 0 keep/shoot tick, 1 racket against statics, 2 puck contacts / sensors, 3 other
 #if defined(HK_FAST_DEBUG) && !defined(__CUDA_ARCH__)
 extern long long g_fast_bail[16];
-#define HK_BAIL(k) do { g_fast_bail[k]++; return false; } while (0)
+#define HK_BAIL(k) do { g_fast_bail[k]++; e.bailKind = (k); return false; } while (0)
 #else
-#define HK_BAIL(k) return false
+#define HK_BAIL(k) do { e.bailKind = (k); return false; } while (0)
 #endif
+HK_HD int bailClass(int kind) {
+  if (kind == 0) return 0;
+  if (kind == 6 || kind == 9 || kind == 8) return 1;
+  if (kind == 2 || kind == 3 || kind == 4 || kind == 10) return 2;
+  return 3;
+}
 
 HK_HD AABB staticCoreAABB(const Scene& S, int f) {  // fat box minus extension and skin (exact enough: eps >> rounding)
   AABB r = S.sfat[f];
@@ -58,7 +66,7 @@ struct FastScratch {
   AABB swept[3];  // tight swept AABB (with shape radius) from this tick's synchronizeFixtures
 };
 
-HK_HD bool collideFast(const Scene& S, const Config& cfg, Env& e) {
+HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, Env& e) {
   int i = 0;
   while (i < e.ncontacts) {
     int pid = clistGet(e.clist, i);
@@ -123,7 +131,7 @@ HK_HD bool collideFast(const Scene& S, const Config& cfg, Env& e) {
 }
 
 // synchronizeFixtures that also keeps the tight swept box; q0 = rotation at the sweep start (== b.q before the move)
-HK_HD void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot q0, AABB* keep) {
+HK_HD_NOINLINE void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot q0, AABB* keep) {
   Body& b = e.b[bi];
   Xf xf1;
   xf1.q = q0;
@@ -139,14 +147,14 @@ HK_HD void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot q0, AABB*
   moveProxy(e, bi, comb, b.p - xf1.p);
 }
 
-HK_HD bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float h) {
+HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float h) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   if (e.moved & 8u) {
     e.moved &= ~8u;
     findNewContacts(S, e);
   }
-  if (!collideFast(S, cfg, e)) return false;
+  if (!collideFast(S, cfg, e)) return false;  // bailKind set by collideFast
   // ---- b2World::Solve with no constraints: every awake body is its own island ----
   FastScratch fs;
   Rot q0[3];

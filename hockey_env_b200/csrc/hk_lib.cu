@@ -108,14 +108,14 @@ struct KParams {
   float4* core;
   uint32_t* cache;
   double* stats;
-  int32_t* queue;    // [2][n] env indices queued for tier 1 (k_mid) and tier 2 (k_long) this tick
-  uint32_t* qctl;    // [0],[1]: tier-1 queue length / finished blocks; [2],[3]: tier-2
+  int32_t* queue;    // [5][n] env indices queued for the general tiers this tick, see Q_* below
+  uint32_t* qctl;    // queue counters, see Q_* below
   int64_t n;
   int64_t env_id_offset;
   Config cfg;
 };
 
-constexpr int kSlowBlock = 64;
+constexpr int kSlowBlock = 384;  // one block per SM at 168 registers: all its warps walk the tick phases together
 
 __global__ void __launch_bounds__(kBlock) k_create(KParams P) {
   __shared__ Scene S;
@@ -167,6 +167,10 @@ __global__ void __launch_bounds__(kBlock) k_step(KParams P, StepIO io) {
 // footprint; every other env index is appended to the tier-1 queue (one atomic per warp).  The general path
 // then runs on compacted queues, so lanes that iterate the contact solver sit next to each other instead of
 // idling 30 neighbours (ncu, round 1: 1.6 active lanes per solver instruction in the monolithic kernel).
+// queue layout: P.queue = [5][n] int32: rows 0-3 = tier-1 work classes (hk_fast.cuh bailClass), row 4 = tier 2.
+// P.qctl = {count[0..3], tier-1 finished blocks, tier-2 count, tier-2 finished blocks, pad}.
+enum { Q_CLASSES = 4, QC_DONE1 = 4, QC_COUNT2 = 5, QC_DONE2 = 6 };
+
 __global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
   __shared__ Scene S;
   stageScene(&S);
@@ -175,80 +179,141 @@ __global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
   TickStats st;
   tickStatsZero(st);
   bool ok = false;
+  int cls = 0;
   if (valid) {
     Env e;
     loadEnv(P.core, P.n, i, e);
+    e.bailKind = 15;
     ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st);
     if (ok) storeEnv(P.core, P.n, i, e);
-    else tickStatsZero(st);
+    else {
+      tickStatsZero(st);
+      cls = bailClass(e.bailKind);
+    }
   }
   const bool need = valid && !ok;
-  const unsigned m = __ballot_sync(0xffffffffu, need);
-  if (m) {
-    const int lane = threadIdx.x & 31;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&P.qctl[0], (unsigned)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (need) P.queue[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+  const int lane = threadIdx.x & 31;
+  if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+    for (int c = 0; c < Q_CLASSES; ++c) {
+      const unsigned m = __ballot_sync(0xffffffffu, need && cls == c);
+      if (m) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&P.qctl[c], (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need && cls == c) P.queue[(int64_t)c * P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+      }
+    }
   }
   flushStats(P.stats, st);
 }
 
-// Tier 2 and 3 of the cascade run the same general path (hk::envTick) over a compacted queue:
+// Tier 1 and 2 of the cascade run the same general path (hk::envTick) over compacted queues:
 //   TIER == 1 (k_mid): budgeted -- a velocity solve must converge (fixed point / short cycle) within kMidSweeps
 //                      sweeps and no continuous-collision EVENT may occur; otherwise the env is appended to the
-//                      next queue with nothing committed;
+//                      tier-2 queue with nothing committed.  Its queue is sorted by work class and every class
+//                      starts on a warp boundary, so the 32 lanes of a warp do the same kind of tick.
 //   TIER == 2 (k_long): unlimited.  Its lanes are the rare long solves and TOI events, packed densely, instead
 //                      of each of them stalling 31 converged neighbours for up to 180 sweeps.
 constexpr int kMidSweeps = 24;
 template <int TIER>
-__global__ void __launch_bounds__(kSlowBlock) k_general(KParams P, StepIO io) {
+__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2) {
   __shared__ Scene S;
   stageScene(&S);
-  uint32_t* ctl = P.qctl + 2 * (TIER - 1);          // [0] length of my queue, [1] my finished blocks
-  const int32_t* myQueue = P.queue + (TIER - 1) * P.n;
-  const unsigned count = *((volatile uint32_t*)&ctl[0]);
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global warp index
+  // Only the first `lanes` lanes of a warp carry an env.  With small batches the general tiers are bound by
+  // per-warp latency (instruction fetch, local memory), not by issue slots: fewer envs per warp means fewer
+  // distinct control-flow paths to serialise and more warps in flight to hide the latency.
+  const int lanes = 1 << lanesLog2;
+  bool valid = false;
+  int64_t i = 0;
+  if (TIER == 1) {
+    int64_t w0 = 0;
+#pragma unroll
+    for (int c = 0; c < Q_CLASSES; ++c) {
+      const unsigned cnt = *((volatile uint32_t*)&P.qctl[c]);
+      const int64_t nw = ((int64_t)cnt + lanes - 1) >> lanesLog2;
+      if (!valid && gw >= w0 && gw < w0 + nw && lane < lanes) {
+        const int64_t j = ((gw - w0) << lanesLog2) + lane;
+        if (j < (int64_t)cnt) {
+          valid = true;
+          i = P.queue[(int64_t)c * P.n + j];
+        }
+      }
+      w0 += nw;
+    }
+  } else {
+    const unsigned cnt = *((volatile uint32_t*)&P.qctl[QC_COUNT2]);
+    const int64_t j = (gw << lanesLog2) + lane;
+    if (lane < lanes && j < (int64_t)cnt) {
+      valid = true;
+      i = P.queue[(int64_t)Q_CLASSES * P.n + j];
+    }
+  }
   TickStats st;
   tickStatsZero(st);
   bool need = false;
-  int64_t i = 0;
-  if (j < (int64_t)count) {
-    i = myQueue[j];
-    Env e;
+  // ---- the tick, phase by phase for the whole block (same code region at the same time on this SM) ----
+  Env e;
+  Cache cache;
+  cache.base = P.cache + i;
+  cache.stride = (size_t)P.n;
+  int had1 = 0, had2 = 0;
+  const uint64_t env_id = (uint64_t)(P.env_id_offset + i);
+  const float dt = (float)(1.0 / HK_FPS);
+  if (valid) {  // phase 1: policy, forces, keep/shoot, Collide
     loadEnv(P.core, P.n, i, e);
-    Cache cache;
-    cache.base = P.cache + i;
-    cache.stride = (size_t)P.n;
-    const bool ok = envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st,
-                            TIER == 1 ? kMidSweeps : (1 << 20), TIER != 1);
-    if (ok) storeEnv(P.core, P.n, i, e);
-    else {
-      tickStatsZero(st);
+    float a[8];
+    policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+    had1 = e.has1;
+    had2 = e.has2;
+    e.sweepBudget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
+    e.allowToiEvents = TIER != 1 || unlimited;
+    e.aborted = false;
+    envStepActions(S, P.cfg, e, a);
+    worldStepCollide(S, P.cfg, cache, e);
+  }
+  __syncthreads();
+  if (valid) solveIslands(S, P.cfg, cache, e, dt, 6 * 30, 2 * 30);  // phase 2
+  __syncthreads();
+  if (valid && !e.aborted && (e.exist & HK_PAIRS_TOI)) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3
+  __syncthreads();
+  if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
+    if (!e.aborted) {
+      worldStepFinish(cache, e);
+      envStepAfterWorld(P.cfg, e);
+      tickFinish(S, P.cfg, e, env_id, (size_t)i, io, true, st, had1, had2);
+      storeEnv(P.core, P.n, i, e);
+    } else {
       need = true;
     }
   }
-  if ((int64_t)blockIdx.x * blockDim.x < (int64_t)count) {
+  if (__any_sync(0xffffffffu, valid)) {
     if (TIER == 1) {
       const unsigned m = __ballot_sync(0xffffffffu, need);
       if (m) {
-        const int lane = threadIdx.x & 31;
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&P.qctl[2], (unsigned)__popc(m));
+        if (lane == 0) base = atomicAdd(&P.qctl[QC_COUNT2], (unsigned)__popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (need) P.queue[P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+        if (need) P.queue[(int64_t)Q_CLASSES * P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
       }
     }
     flushStats(P.stats, st);
   }
-  // the last block to finish re-arms this tier's queue for the next tick
+  // the last block to finish re-arms this tier's queue(s) for the next tick
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    unsigned t = atomicAdd(&ctl[1], 1u);
+    unsigned t = atomicAdd(&P.qctl[TIER == 1 ? QC_DONE1 : QC_DONE2], 1u);
     if (t == gridDim.x - 1) {
-      ctl[0] = 0;
-      ctl[1] = 0;
+      if (TIER == 1) {
+        for (int c = 0; c < Q_CLASSES; ++c) P.qctl[c] = 0;
+        P.qctl[QC_DONE1] = 0;
+      } else {
+        P.qctl[QC_COUNT2] = 0;
+        P.qctl[QC_DONE2] = 0;
+      }
       __threadfence();
     }
   }
@@ -351,6 +416,7 @@ struct hk_env {
   double* stats;
   int32_t* queue;
   uint32_t* qctl;
+  int tiers;  // HK_TIERS=2: fast + unlimited general tier; 3 (default): fast + budgeted + unlimited
   bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
     KParams P;
@@ -365,7 +431,23 @@ struct hk_env {
     return P;
   }
   unsigned grid() const { return (unsigned)((n + kBlock - 1) / kBlock); }
-  unsigned gridSlow() const { return (unsigned)((n + kSlowBlock - 1) / kSlowBlock); }
+  // general tiers with 2^lanesLog2 envs per warp; tier 1: every work class starts on a warp boundary -> up to 4
+  // partly filled extra warps
+  unsigned gridSlow(int lanesLog2, int block) const {
+    int64_t warps = ((n + (1 << lanesLog2) - 1) >> lanesLog2) + 4;
+    return (unsigned)((warps * 32 + block - 1) / block);
+  }
+  // threads per block of the general tiers: as large as possible (the warps of a block walk the tick phases
+  // together and share fetched code) while still giving every SM about two blocks of the expected queue
+  int blockFor(double expectedFraction) const {
+    int64_t lanes = (int64_t)(expectedFraction * (double)n);
+    int64_t b = (lanes / (2 * 148) + 31) / 32 * 32;
+    if (b < 64) b = 64;
+    if (b > kSlowBlock) b = kSlowBlock;
+    if (const char* e = getenv("HK_SLOW_BLOCK")) b = atoi(e);
+    return (int)b;
+  }
+  int lanes1, lanes2;  // log2 envs per warp in tier 1 / tier 2 (HK_LANES1 / HK_LANES2 override)
 };
 
 static bool validPolicy(int p) { return p >= HK_POLICY_EXTERNAL && p <= HK_POLICY_ZERO; }
@@ -403,6 +485,17 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   {
     const char* m = getenv("HK_MONO");
     h->mono = m && m[0] == '1';
+    const char* t = getenv("HK_TIERS");
+    // measured (profiles/README.md): the separate unlimited tier pays off once the batch fills the GPU
+    h->tiers = n_envs >= 200000 ? 3 : 2;
+    if (t && (t[0] == '2' || t[0] == '3')) h->tiers = t[0] - '0';
+    // envs per warp in the general tiers: dense warps once the batch can fill the GPU, sparse ones below that
+    h->lanes1 = 5;  // measured: sparse warps only add instruction-fetch traffic (profiles/README.md)
+    h->lanes2 = 5;
+    if (const char* l1 = getenv("HK_LANES1")) h->lanes1 = atoi(l1);
+    if (const char* l2 = getenv("HK_LANES2")) h->lanes2 = atoi(l2);
+    if (h->lanes1 < 0 || h->lanes1 > 5) h->lanes1 = 5;
+    if (h->lanes2 < 0 || h->lanes2 > 5) h->lanes2 = 5;
   }
   Scene S;
   std::memset(&S, 0, sizeof(S));
@@ -411,9 +504,9 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->cache, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->stats, sizeof(double) * HK_STATS_DIM);
-  if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * 2 * (size_t)n_envs);
-  if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 4);
-  if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 4);
+  if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * 5 * (size_t)n_envs);
+  if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 8);
+  if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
   if (err == cudaSuccess) {
@@ -487,8 +580,10 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
     k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
   } else {
     k_fast<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
-    k_general<1><<<h->gridSlow(), kSlowBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
-    k_general<2><<<h->gridSlow(), kSlowBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+    const int b1 = h->blockFor(0.5), b2 = h->blockFor(0.1);
+    k_general<1><<<h->gridSlow(h->lanes1, b1), b1, 0, (cudaStream_t)stream>>>(h->params(), io, h->tiers == 2 ? 1 : 0, h->lanes1);
+    if (h->tiers == 3)
+      k_general<2><<<h->gridSlow(h->lanes2, b2), b2, 0, (cudaStream_t)stream>>>(h->params(), io, 1, h->lanes2);
   }
   HK_CUDA(cudaGetLastError());
   return HK_OK;

@@ -92,7 +92,7 @@ HK_HD float fabs2(float a) { return a > 0.0f ? a : -a; }
 // sin/cos evaluated in double by a fixed polynomial (fdlibm kernel coefficients, Cody-Waite
 // reduction) and rounded to float: equals the correctly rounded sinf/cosf for all but ~1e-8 of
 // arguments and is bit-identical on host and device (no libm / libdevice dependence).
-HK_HD void sincos_poly(double x, double* s, double* c) {
+HK_HD_NOINLINE void sincos_poly(double x, double* s, double* c) {
   const double kd = rint(x * 0.63661977236758134308);
   const long long k = (long long)kd;
   double r = (x - kd * 1.57079632673412561417e+00) - kd * 6.07710050650619224932e-11;
@@ -195,7 +195,7 @@ HK_HD bool aabbOverlap(const AABB& a, const AABB& b) {
 struct U4 {
   uint32_t x, y, z, w;
 };
-HK_HD U4 philox(uint64_t seed, uint64_t env, uint32_t c2, uint32_t c3) {
+HK_HD_NOINLINE U4 philox(uint64_t seed, uint64_t env, uint32_t c2, uint32_t c3) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)env, c1 = (uint32_t)(env >> 32);
 #pragma unroll

@@ -44,7 +44,7 @@ HK_HD void writeRow18(float* dst, const float* o) {
 
 // everything after the physics of a tick: info/reward, outputs, statistics, auto-reset
 // `write` = false suppresses all per-tick outputs (fused rollout, all but the last tick)
-HK_HD void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io, bool write,
+HK_HD_NOINLINE void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io, bool write,
                       TickStats& st, int had1, int had2) {
   double inf[4], inf2[4];
   getInfo(cfg, e, false, inf);

@@ -84,6 +84,8 @@ struct Env {
   uint64_t pcount;        // 2 bits per pair: manifold point count held in the cache
   // per-step scratch
   uint32_t enabled;
+  float sepBound[N_PAIRS];  // per pair: distance lower bound from this tick's Collide (or -max if not evaluated)
+  bool toiEventSeen;
   Manifold mf[MAX_MANIFOLDS];
   int mfPid[MAX_MANIFOLDS];
   int nmf;
@@ -94,6 +96,7 @@ struct Env {
   int sweepBudget;   // max velocity sweeps a solve may need to converge (>= 180: unlimited)
   bool allowToiEvents;
   bool aborted;
+  int bailKind;  // why the fast path gave up (hk_fast.cuh)
 };
 
 struct Config {
@@ -178,7 +181,7 @@ HK_HD AABB fixtureFat(const Scene& S, const Env& e, int f) { return f < N_STATIC
 HK_HD int staticBodyOf(int f) { return f < 6 ? f : (f < 8 ? 6 : 7); }
 
 // ---- fixture AABB / broad-phase proxy (b2Fixture::Synchronize, b2DynamicTree::MoveProxy) ----------
-HK_HD AABB shapeAABB(const Scene& S, int bi, const Xf& xf) {
+HK_HD_NOINLINE AABB shapeAABB(const Scene& S, int bi, const Xf& xf) {
   AABB r;
   if (bi == B_PUCK) {
     float rad = S.puckRadius;
@@ -215,7 +218,7 @@ HK_HD void moveProxy(Env& e, int bi, const AABB& aabb, V2 displacement) {
   e.fat[bi] = b;
   e.moved |= 1u << bi;
 }
-HK_HD void synchronizeFixtures(const Scene& S, Env& e, int bi) {
+HK_HD_NOINLINE void synchronizeFixtures(const Scene& S, Env& e, int bi) {
   Body& b = e.b[bi];
   Xf xf1;
   xf1.q = rotForBody(bi, b.a0);
@@ -230,7 +233,7 @@ HK_HD void synchronizeFixtures(const Scene& S, Env& e, int bi) {
   moveProxy(e, bi, comb, b.p - xf1.p);
 }
 // b2Body::SetTransform (puck teleport, hockey_env.py:619)
-HK_HD void setTransformPuck(const Scene& S, Env& e, V2 position) {
+HK_HD_NOINLINE void setTransformPuck(const Scene& S, Env& e, V2 position) {
   Body& b = e.b[B_PUCK];
   b.q = rotIdentity();
   b.p = position;
@@ -247,7 +250,7 @@ HK_HD void setTransformPuck(const Scene& S, Env& e, V2 position) {
 }
 
 // b2ContactManager::FindNewContacts for the buffered proxy moves
-HK_HD void findNewContacts(const Scene& S, Env& e) {
+HK_HD_NOINLINE void findNewContacts(const Scene& S, Env& e) {
   uint32_t mv = e.moved & 7u;
   e.moved &= ~7u;
   if (!mv) return;
@@ -304,7 +307,7 @@ HK_HD int findSlot(const Env& e, int pid) {
   return -1;
 }
 
-HK_HD void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
+HK_HD_NOINLINE void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
   int fA = S.pairFA[pid], fB = S.pairFB[pid];
   Xf xfA = fixtureXf(S, e, fA);
   if (fB == F_PUCK) {
@@ -317,7 +320,7 @@ HK_HD void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) 
 // b2Contact::Update.  Manifold ids and warm-start impulses of the contacts handled this tick live in the
 // manifold slots; the global cache is read the first time a pair is updated in a tick and written once, by
 // commitCache(), when the tick completes.
-HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, Env& e, int pid) {
+HK_HD_NOINLINE void updateContact(const Scene& S, const Config& cfg, const Cache& cache, Env& e, int pid) {
   const uint32_t bit = 1u << pid;
   e.enabled |= bit;
   const bool wasTouching = (e.touch & bit) != 0;
@@ -329,6 +332,7 @@ HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, 
     int slot = findSlot(e, pid);
     Manifold tmp;
     evaluateManifold(S, e, pid, &tmp);
+    e.sepBound[pid] = tmp.sepBound;
     touching = tmp.count > 0;
     int oldCount;
     uint32_t oldKey[2] = {0, 0};
@@ -385,7 +389,7 @@ HK_HD void updateContact(const Scene& S, const Config& cfg, const Cache& cache, 
 }
 
 // write the ids / impulses of every manifold handled this tick to the persistent cache (end of a completed tick)
-HK_HD void commitCache(const Cache& cache, const Env& e) {
+HK_HD_NOINLINE void commitCache(const Cache& cache, const Env& e) {
   for (int sIdx = 0; sIdx < e.nmf; ++sIdx) {
     const Manifold& m = e.mf[sIdx];
     const int pid = e.mfPid[sIdx];
@@ -400,7 +404,7 @@ HK_HD void commitCache(const Cache& cache, const Env& e) {
 }
 
 // b2ContactManager::Collide
-HK_HD void collide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
+HK_HD_NOINLINE void collide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   int i = 0;
   while (i < e.ncontacts) {
     int pid = clistGet(e.clist, i);
@@ -494,7 +498,7 @@ HK_HD BodyRef bodyRef(const Scene& S, const Env& e, int fixture) {
 HK_HD float fixtureRadius(const Scene& S, int f) { return f == F_PUCK ? S.puckRadius : HK_POLYGON_RADIUS; }
 
 // b2ContactSolver ctor + InitializeVelocityConstraints for one contact
-HK_HD void initConstraint(const Scene& S, const Env& e, int pid, int slot, bool warmStarting, VC* vc) {
+HK_HD_NOINLINE void initConstraint(const Scene& S, const Env& e, int pid, int slot, bool warmStarting, VC* vc) {
   const Manifold& m = e.mf[slot];
   int fA = S.pairFA[pid], fB = S.pairFB[pid];
   vc->slot = slot;
@@ -588,7 +592,7 @@ HK_HD void storeVel(Env& e, int bi, const Vel& x) {
   }
 }
 
-HK_HD void warmStartConstraint(Env& e, const VC& vc) {
+HK_HD_NOINLINE void warmStartConstraint(Env& e, const VC& vc) {
   Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
   V2 normal = vc.normal;
   V2 tangent = cross(normal, 1.0f);
@@ -605,7 +609,7 @@ HK_HD void warmStartConstraint(Env& e, const VC& vc) {
 }
 
 // one Gauss-Seidel pass over one contact; returns true if any applied impulse increment was non-zero
-HK_HD bool solveVelocityConstraint(Env& e, VC& vc) {
+HK_HD_NOINLINE bool solveVelocityConstraint(Env& e, VC& vc) {
   bool changed = false;
   Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
@@ -712,7 +716,7 @@ struct SolveSnap {
   float v[9];
   float imp[MAX_MANIFOLDS * 4];
 };
-HK_HD void snapSave(const Env& e, const VC* vcs, int nvc, SolveSnap& s) {
+HK_HD_NOINLINE void snapSave(const Env& e, const VC* vcs, int nvc, SolveSnap& s) {
   for (int b = 0; b < 3; ++b) {
     s.v[3 * b] = e.b[b].v.x;
     s.v[3 * b + 1] = e.b[b].v.y;
@@ -725,13 +729,13 @@ HK_HD void snapSave(const Env& e, const VC* vcs, int nvc, SolveSnap& s) {
     s.imp[4 * k + 3] = vcs[k].count > 1 ? vcs[k].pt[1].ti : 0.0f;
   }
 }
-HK_HD bool snapEqual(const SolveSnap& a, const SolveSnap& b, int nvc) {
+HK_HD_NOINLINE bool snapEqual(const SolveSnap& a, const SolveSnap& b, int nvc) {
   bool eq = true;
   for (int i = 0; i < 9; ++i) eq = eq && (a.v[i] == b.v[i]);
   for (int i = 0; i < 4 * nvc; ++i) eq = eq && (a.imp[i] == b.imp[i]);
   return eq;
 }
-HK_HD void snapRestore(Env& e, VC* vcs, int nvc, const SolveSnap& s) {
+HK_HD_NOINLINE void snapRestore(Env& e, VC* vcs, int nvc, const SolveSnap& s) {
   for (int b = 0; b < 3; ++b) {
     e.b[b].v = mk(s.v[3 * b], s.v[3 * b + 1]);
     e.b[b].w = s.v[3 * b + 2];
@@ -745,11 +749,219 @@ HK_HD void snapRestore(Env& e, VC* vcs, int nvc, const SolveSnap& s) {
     }
   }
 }
-#define HK_CYCLE_RING 8
+// Specialised sweep loop for the dominant case -- one contact with one manifold point (95 % of solves): every
+// quantity lives in registers, same expression order as solveVelocityConstraint().
+HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
+  const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
+  const V2 normal = vc.normal;
+  const V2 tangent = cross(normal, 1.0f);
+  const float friction = vc.friction;
+  const V2 rA = vc.pt[0].rA, rB = vc.pt[0].rB;
+  const float normalMass = vc.pt[0].normalMass, tangentMass = vc.pt[0].tangentMass, bias = vc.pt[0].bias;
+  float ni = vc.pt[0].ni, ti = vc.pt[0].ti;
+  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
+  V2 vA = A.v, vB = B.v;
+  float wA = A.w, wB = B.w;
+  // states after the previous sweep (1) and the one before (2)
+  V2 vA1 = vA, vB1 = vB, vA2 = vA, vB2 = vB;
+  float wA1 = wA, wB1 = wB, ni1 = ni, ti1 = ti, wA2 = wA, wB2 = wB, ni2 = ni, ti2 = ti;
+  int it = 0;
+  int result = 0;
+  for (; it < velIters; ++it) {
+    bool changed = false;
+    {
+      V2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
+      float vt = dot(dv, tangent) - 0.0f;
+      float lambda = tangentMass * (-vt);
+      float maxFriction = friction * ni;
+      float newImpulse = fclamp(ti + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - ti;
+      ti = newImpulse;
+      changed = changed || (lambda != 0.0f);
+      V2 P = lambda * tangent;
+      vA -= mA * P;
+      wA -= iA * cross(rA, P);
+      vB += mB * P;
+      wB += iB * cross(rB, P);
+    }
+    {
+      V2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
+      float vn = dot(dv, normal);
+      float lambda = -normalMass * (vn - bias);
+      float newImpulse = fmax2(ni + lambda, 0.0f);
+      lambda = newImpulse - ni;
+      ni = newImpulse;
+      changed = changed || (lambda != 0.0f);
+      V2 P = lambda * normal;
+      vA -= mA * P;
+      wA -= iA * cross(rA, P);
+      vB += mB * P;
+      wB += iB * cross(rB, P);
+    }
+    e.nVelIters++;
+    if (!changed) {
+      result = it + 1;
+      break;
+    }
+    if (it >= 2 && vA.x == vA2.x && vA.y == vA2.y && wA == wA2 && vB.x == vB2.x && vB.y == vB2.y && wB == wB2 &&
+        ni == ni2 && ti == ti2) {
+      // period-2 cycle: state after sweep it+1 == state after sweep it-1
+      const int remaining = velIters - 1 - it;
+      if (remaining & 1) {
+        vA = vA1; vB = vB1; wA = wA1; wB = wB1; ni = ni1; ti = ti1;
+      }
+      result = it + 1;
+      break;
+    }
+    vA2 = vA1; vB2 = vB1; wA2 = wA1; wB2 = wB1; ni2 = ni1; ti2 = ti1;
+    vA1 = vA; vB1 = vB; wA1 = wA; wB1 = wB; ni1 = ni; ti1 = ti;
+    if (it + 1 >= e.sweepBudget && it + 1 < velIters) {
+      result = -1;
+      break;
+    }
+    result = it + 1;
+  }
+  vc.pt[0].ni = ni;
+  vc.pt[0].ti = ti;
+  A.v = vA; A.w = wA; B.v = vB; B.w = wB;
+  storeVel(e, vc.bA, A);
+  storeVel(e, vc.bB, B);
+  return result;
+}
+
+// Same for one contact with a two-point manifold (racket resting on a wall / goal): tangent rows, then the 2x2
+// block solver of b2ContactSolver::SolveVelocityConstraints, all in registers.
+HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
+  const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
+  const V2 normal = vc.normal;
+  const V2 tangent = cross(normal, 1.0f);
+  const float friction = vc.friction;
+  const V2 rA0 = vc.pt[0].rA, rB0 = vc.pt[0].rB, rA1 = vc.pt[1].rA, rB1 = vc.pt[1].rB;
+  const float tm0 = vc.pt[0].tangentMass, tm1 = vc.pt[1].tangentMass;
+  const float nm0 = vc.pt[0].normalMass, nm1 = vc.pt[1].normalMass;
+  const float bias0 = vc.pt[0].bias, bias1 = vc.pt[1].bias;
+  const float k11 = vc.k11, k12 = vc.k12, k22 = vc.k22, n11 = vc.n11, n12 = vc.n12, n21 = vc.n21, n22 = vc.n22;
+  float ni0 = vc.pt[0].ni, ti0 = vc.pt[0].ti, ni1 = vc.pt[1].ni, ti1 = vc.pt[1].ti;
+  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
+  V2 vA = A.v, vB = B.v;
+  float wA = A.w, wB = B.w;
+  // previous (p) and before-previous (q) states
+  V2 vAp = vA, vBp = vB, vAq = vA, vBq = vB;
+  float wAp = wA, wBp = wB, wAq = wA, wBq = wB;
+  float ni0p = ni0, ti0p = ti0, ni1p = ni1, ti1p = ti1, ni0q = ni0, ti0q = ti0, ni1q = ni1, ti1q = ti1;
+  int result = 0;
+  for (int it = 0; it < velIters; ++it) {
+    bool changed = false;
+    {  // tangent, point 0
+      V2 dv = vB + cross(wB, rB0) - vA - cross(wA, rA0);
+      float vt = dot(dv, tangent) - 0.0f;
+      float lambda = tm0 * (-vt);
+      float maxFriction = friction * ni0;
+      float newImpulse = fclamp(ti0 + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - ti0;
+      ti0 = newImpulse;
+      changed = changed || (lambda != 0.0f);
+      V2 P = lambda * tangent;
+      vA -= mA * P;
+      wA -= iA * cross(rA0, P);
+      vB += mB * P;
+      wB += iB * cross(rB0, P);
+    }
+    {  // tangent, point 1
+      V2 dv = vB + cross(wB, rB1) - vA - cross(wA, rA1);
+      float vt = dot(dv, tangent) - 0.0f;
+      float lambda = tm1 * (-vt);
+      float maxFriction = friction * ni1;
+      float newImpulse = fclamp(ti1 + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - ti1;
+      ti1 = newImpulse;
+      changed = changed || (lambda != 0.0f);
+      V2 P = lambda * tangent;
+      vA -= mA * P;
+      wA -= iA * cross(rA1, P);
+      vB += mB * P;
+      wB += iB * cross(rB1, P);
+    }
+    {  // block solver
+      V2 a = mk(ni0, ni1);
+      V2 dv1 = vB + cross(wB, rB0) - vA - cross(wA, rA0);
+      V2 dv2 = vB + cross(wB, rB1) - vA - cross(wA, rA1);
+      float vn1 = dot(dv1, normal);
+      float vn2 = dot(dv2, normal);
+      V2 b;
+      b.x = vn1 - bias0;
+      b.y = vn2 - bias1;
+      b -= mk(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
+      V2 x;
+      bool found = false;
+      x = -mk(n11 * b.x + n12 * b.y, n21 * b.x + n22 * b.y);
+      if (x.x >= 0.0f && x.y >= 0.0f) found = true;
+      if (!found) {
+        x.x = -nm0 * b.x;
+        x.y = 0.0f;
+        vn2 = k12 * x.x + b.y;
+        if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
+      }
+      if (!found) {
+        x.x = 0.0f;
+        x.y = -nm1 * b.y;
+        vn1 = k12 * x.y + b.x;
+        if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
+      }
+      if (!found) {
+        x.x = 0.0f;
+        x.y = 0.0f;
+        vn1 = b.x;
+        vn2 = b.y;
+        if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
+      }
+      if (found) {
+        V2 d = x - a;
+        V2 P1 = d.x * normal, P2 = d.y * normal;
+        vA -= mA * (P1 + P2);
+        wA -= iA * (cross(rA0, P1) + cross(rA1, P2));
+        vB += mB * (P1 + P2);
+        wB += iB * (cross(rB0, P1) + cross(rB1, P2));
+        ni0 = x.x;
+        ni1 = x.y;
+        changed = changed || (d.x != 0.0f) || (d.y != 0.0f);
+      }
+    }
+    e.nVelIters++;
+    result = it + 1;
+    if (!changed) break;
+    if (it >= 2 && vA.x == vAq.x && vA.y == vAq.y && wA == wAq && vB.x == vBq.x && vB.y == vBq.y && wB == wBq &&
+        ni0 == ni0q && ti0 == ti0q && ni1 == ni1q && ti1 == ti1q) {
+      const int remaining = velIters - 1 - it;
+      if (remaining & 1) {
+        vA = vAp; vB = vBp; wA = wAp; wB = wBp; ni0 = ni0p; ti0 = ti0p; ni1 = ni1p; ti1 = ti1p;
+      }
+      break;
+    }
+    vAq = vAp; vBq = vBp; wAq = wAp; wBq = wBp; ni0q = ni0p; ti0q = ti0p; ni1q = ni1p; ti1q = ti1p;
+    vAp = vA; vBp = vB; wAp = wA; wBp = wB; ni0p = ni0; ti0p = ti0; ni1p = ni1; ti1p = ti1;
+    if (it + 1 >= e.sweepBudget && it + 1 < velIters) {
+      result = -1;
+      break;
+    }
+  }
+  vc.pt[0].ni = ni0;
+  vc.pt[0].ti = ti0;
+  vc.pt[1].ni = ni1;
+  vc.pt[1].ti = ti1;
+  A.v = vA; A.w = wA; B.v = vB; B.w = wB;
+  storeVel(e, vc.bA, A);
+  storeVel(e, vc.bB, B);
+  return result;
+}
+
+// general loop: any number of contacts; fixed point and period-2 detection
 // returns the number of sweeps executed, or -1 if the tier's sweep budget ran out before the state repeated
-HK_HD int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
-  SolveSnap ring[HK_CYCLE_RING];  // ring[(sweep index) % RING] = state after that sweep
-  const int kFirstSnap = 3;
+HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
+  if (nvc == 1 && vcs[0].count == 1) return runVelocityIterations1(e, vcs[0], velIters);
+  if (nvc == 1 && vcs[0].count == 2) return runVelocityIterations2(e, vcs[0], velIters);
+  SolveSnap p1, p2;  // states after the previous sweep and the one before
+  const int kFirstSnap = 2;
   int it = 0;
   for (; it < velIters; ++it) {
     bool changed = false;
@@ -762,25 +974,14 @@ HK_HD int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
     if (it >= kFirstSnap) {
       SolveSnap cur;
       snapSave(e, vcs, nvc, cur);
-      int period = 0;
-      for (int p = 2; p <= HK_CYCLE_RING && it - p >= kFirstSnap; ++p) {
-        if (snapEqual(cur, ring[(it - p) % HK_CYCLE_RING], nvc)) {
-          period = p;
-          break;
-        }
-      }
-      if (period) {
-        // state after sweep j (j >= it - period) equals the stored state of sweep it - period + ((j - it) mod period)
+      if (it >= kFirstSnap + 2 && snapEqual(cur, p2, nvc)) {
         const int remaining = velIters - 1 - it;
-        const int r = remaining % period;
-        if (r) snapRestore(e, vcs, nvc, ring[(it - period + r) % HK_CYCLE_RING]);
-#if defined(HK_FAST_DEBUG) && !defined(__CUDA_ARCH__)
-        g_period_hist[period]++;
-#endif
+        if (remaining & 1) snapRestore(e, vcs, nvc, p1);
         ++it;
         break;
       }
-      ring[it % HK_CYCLE_RING] = cur;
+      p2 = p1;
+      p1 = cur;
     }
     if (it + 1 >= e.sweepBudget && it + 1 < velIters) return -1;
   }
@@ -790,7 +991,7 @@ HK_HD int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
 // b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints for one contact.
 // In a TOI island every contact is (static A, the TOI dynamic body B), so the TOI mass rule
 // ("only the two TOI bodies have mass") reduces to the normal masses.
-HK_HD float solvePositionConstraint(const Scene& S, Env& e, int pid, const Manifold& m, int count, bool toi) {
+HK_HD_NOINLINE float solvePositionConstraint(const Scene& S, Env& e, int pid, const Manifold& m, int count, bool toi) {
   float minSeparation = 0.0f;
   int fA = S.pairFA[pid], fB = S.pairFB[pid];
   int bA = fixtureBody(fA), bB = fixtureBody(fB);
@@ -868,7 +1069,7 @@ HK_HD void integratePosition(Body& b, float h) {
 // iterations with a per-island "done" mask (that loop is not a fixed-point iteration, so each island must stop
 // exactly where b2Island::Solve would).  One loop per env instead of one per island keeps the lanes of a warp
 // in the same loop at the same time.
-HK_HD void synchronizeFixturesQ0(const Scene& S, Env& e, int bi, Rot q0) {
+HK_HD_NOINLINE void synchronizeFixturesQ0(const Scene& S, Env& e, int bi, Rot q0) {
   Body& b = e.b[bi];
   Xf xf1;
   xf1.q = q0;
@@ -883,7 +1084,7 @@ HK_HD void synchronizeFixturesQ0(const Scene& S, Env& e, int bi, Rot q0) {
   moveProxy(e, bi, comb, b.p - xf1.p);
 }
 
-HK_HD void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h, int velIters, int posIters) {
+HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h, int velIters, int posIters) {
   (void)cfg;
   e.b[0].island = e.b[1].island = e.b[2].island = false;
   uint32_t inIsland = 0;  // contacts
@@ -1136,7 +1337,24 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
         Sweep sB = bodySweep(S, B, bi);
         int state;
         float t;
-        timeOfImpact(&state, &t, pA, sA, pB, sB, 1.0f);
+        // Exact skip: b2TimeOfImpact can only answer "touching" if the core shapes come within target + tolerance
+        // at some time of the sweep.  sepBound (a face separation from this tick's Collide, evaluated at the sweep
+        // start pose) bounds the start distance from below and no point of the body travels farther than
+        // |dc| + R |da|, so if the difference stays above target + tolerance (+ margin) the answer is alpha = 1.
+        bool skip = false;
+        if (!e.toiEventSeen && alpha0 == 0.0f && B.island) {
+          V2 dc = B.c - B.c0;
+          float disp = length(dc) + (bi == B_PUCK ? 0.0f : 0.5f * fabs2(B.a - B.a0));
+          float totalRadius = pA.radius + pB.radius;
+          float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
+          skip = e.sepBound[pid] - disp > target + 0.25f * HK_LINEAR_SLOP + 0.002f;
+        }
+        if (skip) {
+          state = TOI_SEPARATED;
+          t = 1.0f;
+        } else {
+          timeOfImpact(&state, &t, pA, sA, pB, sB, 1.0f);
+        }
         float beta = t;
         if (state == TOI_TOUCHING) alpha = fmin2(alpha0 + (1.0f - alpha0) * beta, 1.0f);
         else alpha = 1.0f;
@@ -1154,6 +1372,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
       return;
     }
     e.nToiEvents++;
+    e.toiEventSeen = true;
 
     const int fA = S.pairFA[minPid], fB = S.pairFB[minPid];
     const int bi = fB - F_R1;
@@ -1241,24 +1460,34 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
   }
 }
 
-// b2World::Step(dt, velocityIterations, positionIterations)
-HK_HD void worldStep(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float dt, int velIters, int posIters) {
+// b2World::Step(dt, velocityIterations, positionIterations), cut into four phases.  The general kernels run
+// one phase at a time for the whole thread block (hk_lib.cu) so that the warps of an SM execute the same code
+// region together and share instruction-cache lines; worldStep() below is the same sequence in one call.
+HK_HD_NOINLINE void worldStepCollide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
+  e.toiEventSeen = false;
+  for (int k = 0; k < N_PAIRS; ++k) e.sepBound[k] = -HK_MAXFLOAT;
   if (e.moved & 8u) {
     e.moved &= ~8u;
     findNewContacts(S, e);
   }
   collide(S, cfg, cache, e);
-  solveIslands(S, cfg, cache, e, dt, velIters, posIters);
-  if (e.aborted) return;
-  if (e.exist & HK_PAIRS_TOI) solveTOI(S, cfg, cache, e, dt, velIters);
-  if (e.aborted) return;
+}
+HK_HD void worldStepFinish(const Cache& cache, Env& e) {
   commitCache(cache, e);
   for (int bi = 0; bi < 3; ++bi) {  // ClearForces
     e.b[bi].f = mk(0.0f, 0.0f);
     e.b[bi].tq = 0.0f;
   }
+}
+HK_HD_NOINLINE void worldStep(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float dt, int velIters, int posIters) {
+  worldStepCollide(S, cfg, cache, e);
+  solveIslands(S, cfg, cache, e, dt, velIters, posIters);
+  if (e.aborted) return;
+  if (e.exist & HK_PAIRS_TOI) solveTOI(S, cfg, cache, e, dt, velIters);
+  if (e.aborted) return;
+  worldStepFinish(cache, e);
 }
 
 }  // namespace hk

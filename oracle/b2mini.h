@@ -55,7 +55,8 @@ static const int kMaxTOIContacts = 32;
 // b2Rot::Set calls sinf/cosf.  Mode 1 uses libm.  Mode 0 (default) evaluates sin/cos in double
 // with a fixed polynomial and rounds to float: the result is the correctly rounded float in all
 // but ~1e-8 of arguments (tests/test_oracle_trig.py measures this against libm), and -- unlike
-// libm -- is bit-reproducible on the GPU, which lets the CUDA path be compared bit-for-bit.
+// libm -- is bit-reproducible on the GPU, which lets the CUDA path be compared bit-for-bit.  (Measured: the
+// polynomial gives the correctly rounded value; glibc sinf/cosf is 1 ulp off it for ~1 % of arguments.)
 extern int g_trig_mode;
 // Box2D 2.3.0's b2Sweep::Advance computes c0 = (1-beta)*c0 + beta*c, which moves a *static* body's
 // stored centre by an ulp whenever SolveTOI advances it.  0 (default): statics are immovable (only

@@ -929,22 +929,31 @@ int hko_scene_polygon(void* h, int f, float* out) {
 void hko_sincosf(const float* x, int64_t n, float* s, float* c) {
   for (int64_t i = 0; i < n; ++i) sincosf_b2(x[i], s + i, c + i);
 }
-// exhaustive-ish check vs libm: counts arguments in [lo_bits, hi_bits) (raw float bit patterns) where
-// the polynomial sin/cos differ from libm sinf/cosf
-int64_t hko_trig_mismatches(uint32_t lo_bits, uint32_t hi_bits, uint32_t stride) {
-  int64_t bad = 0;
+// sampled check of the polynomial sin/cos over raw float bit patterns [lo_bits, hi_bits) with the given stride (and
+// the negated arguments): out[0] = results that differ from the CORRECTLY ROUNDED value (double libm rounded to
+// float), out[1] = results that differ from libm sinf/cosf, out[2] = the largest such difference in ulps.
+void hko_trig_check(uint32_t lo_bits, uint32_t hi_bits, uint32_t stride, int64_t* out) {
+  out[0] = out[1] = out[2] = 0;
   for (uint64_t u = lo_bits; u < hi_bits; u += stride) {
-    float x = u2f((uint32_t)u);
-    double sd, cd;
-    sincos_poly((double)x, &sd, &cd);
-    if ((float)sd != sinf(x)) ++bad;
-    if ((float)cd != cosf(x)) ++bad;
-    x = -x;
-    sincos_poly((double)x, &sd, &cd);
-    if ((float)sd != sinf(x)) ++bad;
-    if ((float)cd != cosf(x)) ++bad;
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      float x = u2f((uint32_t)u);
+      if (sgn) x = -x;
+      double sd, cd;
+      sincos_poly((double)x, &sd, &cd);
+      float got[2] = {(float)sd, (float)cd};
+      float cr[2] = {(float)std::sin((double)x), (float)std::cos((double)x)};
+      float lm[2] = {sinf(x), cosf(x)};
+      for (int k = 0; k < 2; ++k) {
+        if (got[k] != cr[k]) out[0]++;
+        if (got[k] != lm[k]) {
+          out[1]++;
+          int64_t d = (int64_t)f2u(got[k]) - (int64_t)f2u(lm[k]);
+          if (d < 0) d = -d;
+          if (d > out[2]) out[2] = d;
+        }
+      }
+    }
   }
-  return bad;
 }
 
 }  // extern "C"

@@ -59,8 +59,7 @@ def lib():
         L.hko_scene_polygon.argtypes = [vp, i32, vp]
         L.hko_scene_polygon.restype = i32
         L.hko_sincosf.argtypes = [vp, i64, vp, vp]
-        L.hko_trig_mismatches.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
-        L.hko_trig_mismatches.restype = i64
+        L.hko_trig_check.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, vp]
         _lib = L
     return _lib
 

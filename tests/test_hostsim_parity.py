@@ -1,0 +1,102 @@
+"""CPU tier: the product's device code (hockey_env_b200/csrc/*.cuh compiled for the host by tests/hostsim) against
+the independent oracle, on the full canonical state record, tick by tick.  This is the same comparison the GPU tier
+makes through the C ABI; it runs here because the build container has no GPU.  Exact (float words numerically, so
+that -0.0 == +0.0; see parity_util)."""
+import numpy as np
+import pytest
+
+from parity_util import state_mismatches, outputs_equal
+
+
+def _run(O, H, mode, p1, p2, n, steps, seed, fast, external=False):
+    o = O.OracleBatch(n, mode=mode, seed=seed, env_id_offset=7_000_000_000)
+    h = H.HostSimBatch(n, mode=mode, seed=seed, env_id_offset=7_000_000_000, fast=fast)
+    assert len(state_mismatches(o.get_state(), h.get_state())) == 0
+    rng = np.random.default_rng(seed)
+    for t in range(steps):
+        a = rng.uniform(-1.3, 1.3, (n, 8)).astype(np.float32) if external else None
+        ro = o.step(a, p1, p2, O.STEP_AUTORESET)
+        rh = h.step(a, p1, p2, O.STEP_AUTORESET)
+        assert outputs_equal(ro, rh) == [], f"outputs differ at tick {t}"
+        bad = state_mismatches(o.get_state(), h.get_state())
+        assert len(bad) == 0, f"state differs at tick {t}: {bad[:6].tolist()}"
+    return o, h
+
+
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("mode,p1,p2", [(0, 2, 2), (0, 3, 3), (1, 3, 2), (2, 2, 4), (2, 1, 3)])
+def test_device_code_matches_oracle(oracle, hostsim, mode, p1, p2, fast):
+    o, h = _run(oracle, hostsim, mode, p1, p2, n=96, steps=260, seed=40 + mode, fast=fast)
+    so, sh = o.stats(), h.stats()
+    assert so[0] == sh[0] > 0 and so[12] == sh[12]       # episodes, TOI events
+    assert sh[13] == 0                                     # contact-list / manifold-slot overflows
+    if fast:
+        nfast, nmid, nlong = h.fast_counts()
+        assert nfast > 0 and nmid > 0                     # every tier of the cascade was exercised
+        assert nfast + nmid + nlong == 96 * 260
+
+
+def test_external_actions(oracle, hostsim):
+    _run(oracle, hostsim, 0, 0, 0, n=64, steps=200, seed=9, fast=True, external=True)
+
+
+def test_state_record_roundtrip(oracle, hostsim):
+    """get_state -> set_state is lossless in both implementations and portable between them."""
+    O, H = oracle, hostsim
+    o = O.OracleBatch(64, mode=0, seed=2)
+    for _ in range(150):
+        o.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+    s = o.get_state()
+    h = H.HostSimBatch(64, mode=0, seed=2, fast=True)
+    h.set_state(s)
+    assert len(state_mismatches(s, h.get_state())) == 0
+    o2 = O.OracleBatch(64, mode=0, seed=2)
+    o2.set_state(h.get_state())
+    for t in range(80):
+        ra = o.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+        rb = h.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+        rc = o2.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+        assert outputs_equal(ra, rb) == []
+        assert np.array_equal(ra["obs"], rc["obs"]) and np.array_equal(ra["reward"], rc["reward"])
+    assert len(state_mismatches(o.get_state(), h.get_state())) == 0
+
+
+def test_set_obs_state_matches_reference_semantics(oracle, hostsim):
+    """HockeyEnv.set_state (hockey_env.py:594-608): 18 visible values through the body setters."""
+    O, H = oracle, hostsim
+    rng = np.random.default_rng(0)
+    n = 32
+    st = np.zeros((n, 18))
+    st[:, 0] = rng.uniform(-3.4, -0.6, n); st[:, 1] = rng.uniform(-2, 2, n); st[:, 2] = rng.uniform(-1, 1, n)
+    st[:, 3:6] = rng.uniform(-3, 3, (n, 3))
+    st[:, 6] = rng.uniform(0.6, 3.4, n); st[:, 7] = rng.uniform(-2, 2, n); st[:, 8] = rng.uniform(-1, 1, n)
+    st[:, 9:12] = rng.uniform(-3, 3, (n, 3))
+    st[:, 12] = rng.uniform(-3, 3, n); st[:, 13] = rng.uniform(-2.5, 2.5, n); st[:, 14:16] = rng.uniform(-20, 20, (n, 2))
+    st = st.astype(np.float32).astype(np.float64)
+    o = O.OracleBatch(n, mode=0, seed=1)
+    h = H.HostSimBatch(n, mode=0, seed=1, fast=True)
+    o.set_obs_state(st)
+    h.set_obs_state(st.astype(np.float32))
+    assert np.array_equal(o.get_obs()[0], h.get_obs()[0])
+    assert np.allclose(o.get_obs()[0][:, :16], st[:, :16].astype(np.float32), atol=1e-6)
+    for t in range(40):
+        ra = o.step(None, O.POL_WEAK, O.POL_STRONG, 0)
+        rb = h.step(None, O.POL_WEAK, O.POL_STRONG, 0)
+        assert outputs_equal(ra, rb) == [], t
+    assert len(state_mismatches(o.get_state(), h.get_state())) == 0
+
+
+def test_shard_invariance(oracle, hostsim):
+    """Per-env randomness is keyed on the GLOBAL env id: a batch split into two shards (as two GPUs would hold it)
+    evolves exactly like the unsplit batch."""
+    O, H = oracle, hostsim
+    full = H.HostSimBatch(64, mode=0, seed=5, env_id_offset=1000, fast=True)
+    a = H.HostSimBatch(32, mode=0, seed=5, env_id_offset=1000, fast=True)
+    b = H.HostSimBatch(32, mode=0, seed=5, env_id_offset=1032, fast=True)
+    for _ in range(200):
+        full.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+        a.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+        b.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+    sf = full.get_state()
+    assert np.array_equal(sf[:32], a.get_state()) and np.array_equal(sf[32:], b.get_state())
+    assert np.allclose(full.stats()[:5], a.stats()[:5] + b.stats()[:5])

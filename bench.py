@@ -4,7 +4,8 @@
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle restatement) on the host cores
 
-A "step" is one tick of every env of the batch (one hk_step launch per GPU): physics, contact sensing,
+A "step" is one tick of every env of the batch (one hk_step call per GPU = the kernel cascade k_fast -> k_general):
+physics, contact sensing,
 rewards, observation write, in-kernel BasicOpponents and auto-reset.  Workload (config.workload): 65,536
 NORMAL-mode envs per GPU, strong-vs-strong BasicOpponent (weak scaling: envs are independent, sharded by
 contiguous global env ids, no per-step communication; episode statistics are all-reduced once at the end).
@@ -255,7 +256,8 @@ def main():
                     "d2h_bytes_per_step": n * (72 + 4 + 1 + 16), "steps": args.e2e_steps,
                     "note": "player-1 actions from pinned host memory, obs/reward/done/info to pinned host memory, "
                             "host sync every tick; player 2 = in-kernel strong BasicOpponent"},
-            "gpu_launches": args.steps,
+            # kernels of this repo launched in the timed region: k_fast + the general tier(s) per tick
+            "gpu_launches": args.steps * (3 if (n >= 200000 and os.environ.get("HK_TIERS") != "2") or os.environ.get("HK_TIERS") == "3" else 2),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,

@@ -191,3 +191,99 @@ def test_single_env_drop_in_classes(oracle):
         hk.HockeyEnv(mode="NOPE")
     with pytest.raises(TypeError):
         hk.HockeyEnv(mode=1.5)
+
+
+def test_pipeline_variants_are_identical(oracle):
+    """The kernel cascade (fast tier / budgeted tier / unlimited tier) is an execution strategy, not a numerical
+    choice: monolithic kernel, 2-tier and 3-tier pipelines produce identical states."""
+    import os
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    n = 4096
+    envs = []
+    for var in ({"HK_MONO": "1"}, {"HK_TIERS": "2"}, {"HK_TIERS": "3"}):
+        old = {k: os.environ.get(k) for k in ("HK_MONO", "HK_TIERS")}
+        for k in ("HK_MONO", "HK_TIERS"):
+            os.environ.pop(k, None)
+        os.environ.update(var)
+        try:
+            envs.append(hk.HockeyVecEnv(n, device="cuda:0", seed=31, p1="strong", p2="strong"))
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None)
+                if v is not None:
+                    os.environ[k] = v
+    for _ in range(300):
+        for e in envs:
+            e.step()
+    ref = _state(envs[0])
+    for e in envs[1:]:
+        assert len(state_mismatches(ref, _state(e))) == 0
+    s = [e.stats() for e in envs]
+    assert s[0]["episodes"] == s[1]["episodes"] == s[2]["episodes"] > 0
+    assert s[0]["toi_events"] == s[1]["toi_events"] == s[2]["toi_events"]
+
+
+def test_shard_invariance_gpu(oracle):
+    """Two shards with global env-id offsets (what two ranks hold) == one batch: per-env RNG is keyed on global ids."""
+    import hockey_env_b200 as hk
+    n = 2048
+    full = hk.HockeyVecEnv(2 * n, device="cuda:0", seed=8, env_id_offset=10_000, p1="strong", p2="weak")
+    a = hk.HockeyVecEnv(n, device="cuda:0", seed=8, env_id_offset=10_000, p1="strong", p2="weak")
+    b = hk.HockeyVecEnv(n, device="cuda:0", seed=8, env_id_offset=10_000 + n, p1="strong", p2="weak")
+    for _ in range(260):
+        full.step(); a.step(); b.step()
+    sf = _state(full)
+    assert np.array_equal(sf[:n], _state(a)) and np.array_equal(sf[n:], _state(b))
+    sa, sb, s = a.stats(), b.stats(), full.stats()
+    for k in ("episodes", "wins", "losses", "draws", "env_steps", "toi_events"):
+        assert sa[k] + sb[k] == s[k]
+
+
+def test_statistics_vs_notebook_10k_episodes(oracle):
+    """>= 10k episodes of strong-vs-strong BasicOpponent play on the GPU against the reference's recorded 1000-game
+    sample (Hockey-Env.ipynb cells 52-59): W/D/L 319/368/313, mean length 150.9, reward sums."""
+    import json
+    import os
+    import hockey_env_b200 as hk
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_fixtures.json")))["strong_vs_strong_1000_games"]
+    n = 8192
+    env = hk.HockeyVecEnv(n, device="cuda:0", seed=2024, p1="strong", p2="strong", want_agent_two=True)
+    env.reset(one_starting=(torch.arange(n, device="cuda:0") % 2).to(torch.int8))
+    for _ in range(2600):
+        env.step()
+    s = env.stats()
+    ep = s["episodes"]
+    assert ep >= 10_000 and s["overflows"] == 0
+    for got, ref in ((s["wins"] / ep, fx["winners_plus1"] / 1000), (s["draws"] / ep, fx["winners_zero"] / 1000),
+                     (s["losses"] / ep, fx["winners_minus1"] / 1000)):
+        se = np.sqrt(ref * (1 - ref) / 1000 + ref * (1 - ref) / ep)
+        assert abs(got - ref) < 3.5 * se, (got, ref)
+    assert abs(s["sum_episode_len"] / ep - fx["total_steps"] / 1000) < 8.0
+    assert abs(s["wins"] - s["losses"]) / ep < 0.03
+    # reward sums per 1000 games (notebook: -4360 / -4368)
+    assert abs(1000 * s["sum_return_p1"] / ep - fx["reward_sums"][0]) < 500
+    assert abs(1000 * s["sum_return_p2"] / ep - fx["reward_sums"][1]) < 500
+
+
+def test_full_size_invariants():
+    """BASELINE.json's headline size (65,536 NORMAL envs): size-independent properties after 300 ticks."""
+    import hockey_env_b200 as hk
+    n = 65536
+    env = hk.HockeyVecEnv(n, device="cuda:0", seed=1, p1="strong", p2="strong", want_agent_two=True)
+    n_done = 0
+    for t in range(300):
+        obs, rew, done, trunc, info = env.step()
+        n_done += int(done.sum().item())
+        if t % 50 == 49:
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            assert (obs[:, 0] < 0.6).all() and (obs[:, 6] > -0.6).all()          # rackets stay in their halves
+            assert (obs[:, [1, 7]].abs() < 3.6).all()
+            assert ((obs[:, 16] >= 0) & (obs[:, 16] <= 15)).all()
+            w = info["winner"]
+            assert ((w == 0) | (done == 1)).all()                                # a winner implies done
+            assert torch.equal(env.obs2[:, 0], -obs[:, 6]) and torch.equal(env.obs2[:, 2], obs[:, 8])  # mirror identity
+            assert not trunc.any()
+    s = env.stats()
+    assert s["env_steps"] == n * 300 and s["episodes"] == n_done and s["overflows"] == 0
+    assert s["wins"] + s["losses"] + s["draws"] == s["episodes"]

@@ -18,7 +18,7 @@ STEP_AUTORESET = 1
 
 EXPORTS = [
     "hk_create", "hk_destroy", "hk_num_envs", "hk_reset", "hk_step", "hk_rollout", "hk_get_obs", "hk_get_info", "hk_get_state",
-    "hk_set_state", "hk_set_obs_state", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_last_error",
+    "hk_set_state", "hk_set_obs_state", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_last_error",
     "hk_version",
 ]
 
@@ -59,6 +59,8 @@ def load():
     L.hk_get_info.restype = i32
     L.hk_copy_stats.argtypes = [vp, vp, vp]
     L.hk_copy_stats.restype = i32
+    L.hk_debug_phase_cycles.argtypes = [vp, vp]
+    L.hk_debug_phase_cycles.restype = i32
     L.hk_get_state.argtypes = [vp, vp, vp]
     L.hk_get_state.restype = i32
     L.hk_set_state.argtypes = [vp, vp, vp]

@@ -19,7 +19,8 @@ HK_HD uint32_t makeKey(int indexA, int indexB, int typeA, int typeB) {
 
 struct Manifold {
   int type, count;
-  float sepBound;  // lower bound of the core-shape distance at the evaluated poses (max face separation seen)
+  float sepBound;  // lower bound of the core-shape distance at the evaluated poses: separation along sepNormal
+  V2 sepNormal;    // face normal of polygon A (in A's frame) that achieves sepBound
   V2 localNormal, localPoint;
   V2 lp[2];
   uint32_t key[2];
@@ -33,6 +34,7 @@ HK_HD V2 polyN(const Poly& p, int i) { return mk(p.nx[i], p.ny[i]); }
 HK_HD_NOINLINE void collidePolygonCircle(Manifold* m, const Poly& polyA, const Xf& xfA, V2 circleCenterWorld, float circleRadius) {
   m->count = 0;
   m->sepBound = -HK_MAXFLOAT;
+  m->sepNormal = mk(0.0f, 0.0f);
   V2 cLocal = mulT(xfA, circleCenterWorld);
   int normalIndex = 0;
   float separation = -HK_MAXFLOAT;
@@ -42,6 +44,7 @@ HK_HD_NOINLINE void collidePolygonCircle(Manifold* m, const Poly& polyA, const X
     float s = dot(polyN(polyA, i), cLocal - polyV(polyA, i));
     if (s > radius) {
       m->sepBound = s;
+      m->sepNormal = polyN(polyA, i);
       return;
     }
     if (s > separation) {
@@ -53,6 +56,7 @@ HK_HD_NOINLINE void collidePolygonCircle(Manifold* m, const Poly& polyA, const X
   int vertIndex2 = vertIndex1 + 1 < vertexCount ? vertIndex1 + 1 : 0;
   V2 v1 = polyV(polyA, vertIndex1), v2 = polyV(polyA, vertIndex2);
   m->sepBound = separation;
+  m->sepNormal = polyN(polyA, normalIndex);
   m->type = MANIFOLD_FACE_A;
   m->lp[0] = mk(0.0f, 0.0f);
   m->key[0] = 0;
@@ -179,11 +183,12 @@ HK_HD_NOINLINE void collidePolygons(Manifold* m, const Poly& polyA, const Xf& xf
   const float totalRadius = HK_POLYGON_RADIUS + HK_POLYGON_RADIUS;
   int edgeA = 0;
   float separationA = findMaxSeparation(&edgeA, polyA, xfA, polyB, xfB);
-  m->sepBound = separationA;  // any face separation is a lower bound of the distance between the convex cores
+  // a face separation of A is a lower bound of the distance between the convex cores, along that face normal
+  m->sepBound = separationA;
+  m->sepNormal = polyN(polyA, edgeA);
   if (separationA > totalRadius) return;
   int edgeB = 0;
   float separationB = findMaxSeparation(&edgeB, polyB, xfB, polyA, xfA);
-  m->sepBound = fmax2(separationA, separationB);
   if (separationB > totalRadius) return;
   const float k_relativeTol = 0.98f;
   const float k_absoluteTol = 0.001f;

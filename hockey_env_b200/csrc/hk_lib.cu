@@ -110,6 +110,7 @@ struct KParams {
   double* stats;
   int32_t* queue;    // [5][n] env indices queued for the general tiers this tick, see Q_* below
   uint32_t* qctl;    // queue counters, see Q_* below
+  unsigned long long* phaseClk;  // [2 tiers][4 phases] block-cycles spent per phase (diagnostics, hk_debug_phase_cycles)
   int64_t n;
   int64_t env_id_offset;
   Config cfg;
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   int had1 = 0, had2 = 0;
   const uint64_t env_id = (uint64_t)(P.env_id_offset + i);
   const float dt = (float)(1.0 / HK_FPS);
+  long long tc0 = clock64();
   if (valid) {  // phase 1: policy, forces, keep/shoot, Collide
     loadEnv(P.core, P.n, i, e);
     float a[8];
@@ -275,10 +277,13 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     worldStepCollide(S, P.cfg, cache, e);
   }
   __syncthreads();
+  long long tc1 = clock64();
   if (valid) solveIslands(S, P.cfg, cache, e, dt, 6 * 30, 2 * 30);  // phase 2
   __syncthreads();
+  long long tc2 = clock64();
   if (valid && !e.aborted && (e.exist & HK_PAIRS_TOI)) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3
   __syncthreads();
+  long long tc3 = clock64();
   if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
     if (!e.aborted) {
       worldStepFinish(cache, e);
@@ -304,6 +309,14 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   // the last block to finish re-arms this tier's queue(s) for the next tick
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (__any_sync(1u, valid) || true) {
+      long long tc4 = clock64();
+      unsigned long long* pc = P.phaseClk + 4 * (TIER - 1);
+      atomicAdd(&pc[0], (unsigned long long)(tc1 - tc0));
+      atomicAdd(&pc[1], (unsigned long long)(tc2 - tc1));
+      atomicAdd(&pc[2], (unsigned long long)(tc3 - tc2));
+      atomicAdd(&pc[3], (unsigned long long)(tc4 - tc3));
+    }
     __threadfence();
     unsigned t = atomicAdd(&P.qctl[TIER == 1 ? QC_DONE1 : QC_DONE2], 1u);
     if (t == gridDim.x - 1) {
@@ -416,6 +429,7 @@ struct hk_env {
   double* stats;
   int32_t* queue;
   uint32_t* qctl;
+  unsigned long long* phaseClk;
   int tiers;  // HK_TIERS=2: fast + unlimited general tier; 3 (default): fast + budgeted + unlimited
   bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
@@ -425,6 +439,7 @@ struct hk_env {
     P.stats = stats;
     P.queue = queue;
     P.qctl = qctl;
+    P.phaseClk = phaseClk;
     P.n = n;
     P.env_id_offset = env_id_offset;
     P.cfg = cfg;
@@ -482,6 +497,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   h->stats = nullptr;
   h->queue = nullptr;
   h->qctl = nullptr;
+  h->phaseClk = nullptr;
   {
     const char* m = getenv("HK_MONO");
     h->mono = m && m[0] == '1';
@@ -507,6 +523,8 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * 5 * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 8);
+  if (err == cudaSuccess) err = cudaMalloc(&h->phaseClk, sizeof(unsigned long long) * 8);
+  if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
   if (err == cudaSuccess) {
@@ -521,6 +539,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     cudaFree(h->stats);
     cudaFree(h->queue);
     cudaFree(h->qctl);
+    cudaFree(h->phaseClk);
     delete h;
     return fail(HK_E_CUDA, msg);
   }
@@ -536,6 +555,7 @@ int hk_destroy(hk_env* h) {
   cudaFree(h->stats);
   cudaFree(h->queue);
   cudaFree(h->qctl);
+  cudaFree(h->phaseClk);
   delete h;
   return HK_OK;
 }
@@ -665,6 +685,15 @@ int hk_copy_stats(hk_env* h, double* dst_dev, void* stream) {
   if (!h || !dst_dev) return fail(HK_E_INVALID, "hk_copy_stats: NULL argument");
   DeviceGuard guard(h->device);
   HK_CUDA(cudaMemcpyAsync(dst_dev, h->stats, sizeof(double) * HK_STATS_DIM, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return HK_OK;
+}
+
+int hk_debug_phase_cycles(hk_env* h, double* out_host8) {
+  if (!h || !out_host8) return fail(HK_E_INVALID, "hk_debug_phase_cycles: NULL argument");
+  DeviceGuard guard(h->device);
+  unsigned long long v[8];
+  HK_CUDA(cudaMemcpy(v, h->phaseClk, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 8; ++k) out_host8[k] = (double)v[k];
   return HK_OK;
 }
 

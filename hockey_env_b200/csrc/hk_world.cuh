@@ -22,11 +22,14 @@ namespace hk {
 extern long long g_iter_hist[2][182];
 extern long long g_nvc_hist[16];
 extern long long g_period_hist[16];
+extern long long g_toi_dbg[16];
+#define HK_TOI_DBG(k) g_toi_dbg[k]++
 #define HK_ITER_HIST(w, n) g_iter_hist[w][n]++
 #define HK_NVC_HIST(n) g_nvc_hist[n]++
 #else
 #define HK_ITER_HIST(w, n)
 #define HK_NVC_HIST(n)
+#define HK_TOI_DBG(k)
 #endif
 
 enum { MAX_MANIFOLDS = 8, MAX_CLIST = 12 };
@@ -85,7 +88,9 @@ struct Env {
   // per-step scratch
   uint32_t enabled;
   float sepBound[N_PAIRS];  // per pair: distance lower bound from this tick's Collide (or -max if not evaluated)
+  V2 sepNormal[N_PAIRS];    // ... along this world-space face normal of the static polygon
   bool toiEventSeen;
+  AABB swept[3];  // tight swept AABB (incl. shape radius) of each body from this tick's island solve
   Manifold mf[MAX_MANIFOLDS];
   int mfPid[MAX_MANIFOLDS];
   int nmf;
@@ -333,6 +338,7 @@ HK_HD_NOINLINE void updateContact(const Scene& S, const Config& cfg, const Cache
     Manifold tmp;
     evaluateManifold(S, e, pid, &tmp);
     e.sepBound[pid] = tmp.sepBound;
+    e.sepNormal[pid] = tmp.sepNormal;  // statics have angle 0: local normal == world normal
     touching = tmp.count > 0;
     int oldCount;
     uint32_t oldKey[2] = {0, 0};
@@ -1081,6 +1087,7 @@ HK_HD_NOINLINE void synchronizeFixturesQ0(const Scene& S, Env& e, int bi, Rot q0
   comb.ly = fmin2(a1.ly, a2.ly);
   comb.hx = fmax2(a1.hx, a2.hx);
   comb.hy = fmax2(a1.hy, a2.hy);
+  e.swept[bi] = comb;
   moveProxy(e, bi, comb, b.p - xf1.p);
 }
 
@@ -1277,8 +1284,11 @@ HK_HD void bodyAdvance(const Scene& S, Body& b, int bi, float alpha) {  // b2Bod
 }
 
 HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float dt, int velIters) {
+  HK_TOI_DBG(10);
   float salpha[8];  // alpha0 of the 8 static bodies (statics are immovable: only alpha0 advances)
   for (int i = 0; i < 8; ++i) salpha[i] = 0.0f;
+  // bodies that went through this tick's island solve: their sweep start (c0, a0) is the pose Collide saw
+  const uint32_t solvedMask = (e.b[0].island ? 1u : 0u) | (e.b[1].island ? 2u : 0u) | (e.b[2].island ? 4u : 0u);
   e.b[0].island = e.b[1].island = e.b[2].island = false;
   e.b[0].alpha0 = e.b[1].alpha0 = e.b[2].alpha0 = 0.0f;
   uint32_t toiFlag = 0;
@@ -1338,22 +1348,47 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
         int state;
         float t;
         // Exact skip: b2TimeOfImpact can only answer "touching" if the core shapes come within target + tolerance
-        // at some time of the sweep.  sepBound (a face separation from this tick's Collide, evaluated at the sweep
-        // start pose) bounds the start distance from below and no point of the body travels farther than
-        // |dc| + R |da|, so if the difference stays above target + tolerance (+ margin) the answer is alpha = 1.
+        // at some time of the sweep.  sepBound is the separation of the moving shape from a face plane of the
+        // static polygon at the sweep start pose (from this tick's Collide), hence a lower bound of the distance;
+        // along that face normal n no point of the body approaches the plane by more than max(0, -n.dc) + R |da|
+        // (linear centre motion, |r| <= R = 0.5 m from the centre of mass).  If what remains stays above
+        // target + tolerance (+ margin) the answer is alpha = 1.
         bool skip = false;
-        if (!e.toiEventSeen && alpha0 == 0.0f && B.island) {
+        if (!e.toiEventSeen && alpha0 == 0.0f && ((solvedMask >> bi) & 1u)) {
           V2 dc = B.c - B.c0;
-          float disp = length(dc) + (bi == B_PUCK ? 0.0f : 0.5f * fabs2(B.a - B.a0));
+          float toward = -dot(e.sepNormal[pid], dc);
+          float disp = fmax2(toward, 0.0f) + (bi == B_PUCK ? 0.0f : 0.5f * fabs2(B.a - B.a0));
           float totalRadius = pA.radius + pB.radius;
           float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
           skip = e.sepBound[pid] - disp > target + 0.25f * HK_LINEAR_SLOP + 0.002f;
+          if (!skip) {
+            // second proof (same as the fast tier): the swept core AABB of the body stays clear of the static core AABB
+            float r = pB.radius;
+            float da = fabs2(B.a - B.a0);
+            if (bi == B_PUCK || da <= 0.2f) {
+              float sag = bi == B_PUCK ? 0.0f : 0.0625f * da * da;
+              AABB st = S.sfat[fA];
+              const float d = HK_AABB_EXTENSION + HK_POLYGON_RADIUS;
+              st.lx += d; st.ly += d; st.hx -= d; st.hy -= d;
+              AABB mv = e.swept[bi];
+              mv.lx += r; mv.ly += r; mv.hx -= r; mv.hy -= r;
+              float gx = fmax2(st.lx - mv.hx, mv.lx - st.hx), gy = fmax2(st.ly - mv.hy, mv.ly - st.hy);
+              skip = fmax2(gx, gy) > target + 0.25f * HK_LINEAR_SLOP + sag + 0.005f;
+            }
+          }
         }
+        HK_TOI_DBG(bi == B_PUCK ? 0 : 1);
         if (skip) {
           state = TOI_SEPARATED;
           t = 1.0f;
+          HK_TOI_DBG(bi == B_PUCK ? 2 : 3);
         } else {
           timeOfImpact(&state, &t, pA, sA, pB, sB, 1.0f);
+          HK_TOI_DBG(bi == B_PUCK ? 4 : 5);
+          if (e.toiEventSeen) HK_TOI_DBG(6);
+          else if (!(alpha0 == 0.0f && ((solvedMask >> bi) & 1u))) HK_TOI_DBG(7);
+          else if (e.sepBound[pid] == -HK_MAXFLOAT) HK_TOI_DBG(8);
+          if (state == TOI_TOUCHING) HK_TOI_DBG(9);
         }
         float beta = t;
         if (state == TOI_TOUCHING) alpha = fmin2(alpha0 + (1.0f - alpha0) * beta, 1.0f);

@@ -150,6 +150,10 @@ int hk_stats_device_ptr(hk_env* env, double** out_dev);
 /* Device-to-device copy of the accumulators into a caller-owned f64[HK_STATS_DIM] buffer (async). */
 int hk_copy_stats(hk_env* env, double* dst_dev, void* stream);
 
+/* Diagnostics: block-cycles the general tiers spent in each tick phase since creation (synchronises the device).
+ * out_host8 = tier 1 {policy+Collide, island solve, TOI, finish}, tier 2 {same}. */
+int hk_debug_phase_cycles(hk_env* env, double* out_host8);
+
 const char* hk_last_error(void);
 const char* hk_version(void);
 

@@ -1,0 +1,19 @@
+"""Prints the share of block-cycles the general tiers spend in each tick phase (diagnostics)."""
+import ctypes as C
+import sys
+import torch
+sys.path.insert(0, ".")
+import hockey_env_b200 as hk
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+env = hk.HockeyVecEnv(n, device="cuda:0", seed=0, p1="strong", p2="strong")
+env.reset(one_starting=(torch.arange(n, device="cuda:0") % 2).to(torch.int8))
+for _ in range(300):
+    env.step()
+torch.cuda.synchronize()
+out = (C.c_double * 8)()
+hk._lib.check(env.L.hk_debug_phase_cycles(env._h, out))
+v = list(out)
+for t in range(2):
+    tot = sum(v[4 * t:4 * t + 4]) or 1.0
+    print(f"tier {t + 1}: " + "  ".join(f"{name} {100 * v[4 * t + k] / tot:5.1f}%" for k, name in enumerate(("policy+collide", "island-solve", "TOI", "finish"))), f" total {tot:.3g} block-cycles")

@@ -8,7 +8,7 @@
 #include <cstring>
 #include <vector>
 #define HK_FAST_DEBUG 1
-namespace hk { long long g_fast_bail[16]; long long g_iter_hist[2][182]; long long g_nvc_hist[16]; long long g_period_hist[16]; int g_dbg_left = 5; }
+namespace hk { long long g_fast_bail[16]; long long g_iter_hist[2][182]; long long g_nvc_hist[16]; long long g_period_hist[16]; long long g_toi_dbg[16]; int g_dbg_left = 0; }
 #include "../../include/hockey_b200.h"
 #include "../../hockey_env_b200/csrc/hk_tick.cuh"
 
@@ -86,6 +86,7 @@ void hs_step(void* h, const float* action, int stride, int pol1, int pol2, int f
 }
 void hs_bail_counts(long long* out) { for (int i = 0; i < 16; ++i) out[i] = hk::g_fast_bail[i]; }
 void hs_iter_hist(long long* out) { for (int w = 0; w < 2; ++w) for (int i = 0; i < 182; ++i) out[w * 182 + i] = hk::g_iter_hist[w][i]; for (int i = 0; i < 16; ++i) out[364 + i] = hk::g_period_hist[i]; }
+void hs_toi_dbg(long long* out) { for (int i = 0; i < 16; ++i) out[i] = hk::g_toi_dbg[i]; }
 void hs_set_fast(void* h, int on) { ((HostBatch*)h)->use_fast = on; }
 void hs_fast_counts(void* h, long long* out) { out[0] = ((HostBatch*)h)->nFast; out[1] = ((HostBatch*)h)->nSlow; out[2] = ((HostBatch*)h)->nLong; }
 void hs_set_mid_budget(void* h, int b) { ((HostBatch*)h)->mid_budget = b; }

@@ -27,6 +27,9 @@ ENVS_PER_GPU = 65536
 # algorithmic bytes per env-step of the dominant kernel (DESIGN.md "Data layout"): 256 B state read + 256 B state
 # written + obs 72 + reward 4 + done 1 + info 16 (in-kernel opponents: no action read)
 ALGO_BYTES_PER_ENV_STEP = 256 + 256 + 72 + 4 + 1 + 16
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_general<1>) for one launch at 65,536 envs, from the
+# `ncu --set full` capture summarised in profiles/r1_final_raw_metrics.csv (48.0 MB read + 53.0 MB written)
+NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 = 100_974_848
 
 
 def _peaks():
@@ -260,10 +263,12 @@ def main():
             "gpu_launches": args.steps * (3 if (n >= 200000 and os.environ.get("HK_TIERS") != "2") or os.environ.get("HK_TIERS") == "3" else 2),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 if n == 65536 else None,
+                         "traffic_unit": "bytes per launch of the dominant kernel k_general<1> (ncu, profiles/)",
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                         "note": "the kernel is issue/latency-bound, not HBM-bound (DESIGN.md); see profiles/ for "
-                                 "issue-slot utilisation"},
+                         "note": "achieved = algorithmic bytes of one tick (all kernels of the cascade) / tick time; the path "
+                                 "is instruction-fetch/divergence bound, not HBM-bound (DESIGN.md section 4, profiles/README.md)"},
             "episode_stats": {"episodes": st[0], "wins": st[1], "losses": st[2], "draws": st[3], "env_steps": st[4],
                               "mean_len": st[8] / max(st[0], 1), "velocity_iters_per_step": st[11] / max(st[4], 1),
                               "toi_events_per_step": st[12] / max(st[4], 1), "overflows": st[13]},

@@ -281,9 +281,50 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   if (valid) solveIslands(S, P.cfg, cache, e, dt, 6 * 30, 2 * 30);  // phase 2
   __syncthreads();
   long long tc2 = clock64();
-  if (valid && !e.aborted && (e.exist & HK_PAIRS_TOI)) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3
+  // phase 3a-3c: first-pass TOI evaluations of the whole block as one task list, one task per thread
+  const bool wantToi = valid && !e.aborted && (e.exist & HK_PAIRS_TOI);
+  {
+    constexpr int kTasksPerLane = 3;
+    __shared__ ToiTask sTasks[kSlowBlock * kTasksPerLane];  // worst case: every lane files all its tasks
+    __shared__ float sAlpha[kSlowBlock * kTasksPerLane];
+    __shared__ int sCount;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+    ToiTask mine[kTasksPerLane];
+    int nMine = 0, base = 0;
+    if (wantToi) {
+      nMine = toiCollect(S, e, mine, kTasksPerLane);
+      if (nMine > 0) {
+        base = atomicAdd(&sCount, nMine);
+        for (int k = 0; k < nMine; ++k) sTasks[base + k] = mine[k];
+      }
+    }
+    __syncthreads();
+    const int total = sCount;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) sAlpha[t] = toiTaskRun(S, sTasks[t]);
+    __syncthreads();
+    for (int k = 0; k < nMine; ++k) {
+      e.toiPre[mine[k].pid] = sAlpha[base + k];
+      e.toiPreFlag |= 1u << mine[k].pid;
+    }
+  }
+  if (wantToi) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3d: events (rare) on top of the pre-seeded results
   __syncthreads();
   long long tc3 = clock64();
+  {  // diagnostics: block-wide max of per-lane TOI evaluation / event cycles
+    __shared__ unsigned long long sMaxEval, sMaxEvent;
+    if (threadIdx.x == 0) { sMaxEval = 0; sMaxEvent = 0; }
+    __syncthreads();
+    if (valid) {
+      atomicMax(&sMaxEval, (unsigned long long)e.dbgEvalClk);
+      atomicMax(&sMaxEvent, (unsigned long long)e.dbgEventClk);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && TIER == 1) {
+      atomicAdd(&P.phaseClk[4], sMaxEval);
+      atomicAdd(&P.phaseClk[5], sMaxEvent);
+    }
+  }
   if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
     if (!e.aborted) {
       worldStepFinish(cache, e);

@@ -124,6 +124,8 @@ HK_HD void groupsToEnv(const F4* g, Env& e) {
   e.sweepBudget = 1 << 20;
   e.allowToiEvents = true;
   e.aborted = false;
+  e.dbgEvalClk = e.dbgEventClk = 0;
+  e.toiPreFlag = 0;
 }
 
 // ---- canonical record <-> Env ------------------------------------------------------------------
@@ -272,6 +274,8 @@ HK_HD void unpackRecord(const uint32_t* r, Env& e, const Cache& cache) {
   e.sweepBudget = 1 << 20;
   e.allowToiEvents = true;
   e.aborted = false;
+  e.dbgEvalClk = e.dbgEventClk = 0;
+  e.toiPreFlag = 0;
 }
 
 // HockeyEnv.set_state (hockey_env.py:594-608): 18 visible values; goes through b2Body::SetTransform

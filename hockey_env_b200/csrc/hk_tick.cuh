@@ -141,6 +141,8 @@ HK_HD void envCreate(const Scene& S, const Config& cfg, Env& e, uint64_t env_id)
   e.sweepBudget = 1 << 20;
   e.allowToiEvents = true;
   e.aborted = false;
+  e.dbgEvalClk = e.dbgEventClk = 0;
+  e.toiPreFlag = 0;
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   U4 r = philox(cfg.seed, env_id, 0, HK_STREAM_PHASE0);

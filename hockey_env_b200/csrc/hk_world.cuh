@@ -91,11 +91,14 @@ struct Env {
   V2 sepNormal[N_PAIRS];    // ... along this world-space face normal of the static polygon
   bool toiEventSeen;
   AABB swept[3];  // tight swept AABB (incl. shape radius) of each body from this tick's island solve
+  uint32_t toiPreFlag;      // pairs whose first-pass TOI was computed ahead of solveTOI (block-wide task pass)
+  float toiPre[N_PAIRS];
   Manifold mf[MAX_MANIFOLDS];
   int mfPid[MAX_MANIFOLDS];
   int nmf;
   // counters (statistics)
   uint32_t nVelIters, nToiEvents, nOverflow;
+  long long dbgEvalClk, dbgEventClk;  // diagnostics: cycles this lane spent in TOI evaluation / event handling
   // budgets of this tier (hk_lib.cu cascade); exceeding one sets `aborted` and the tick is redone, from the
   // stored state, by the next tier.  Nothing is committed before the end of a tick, so aborting is free.
   int sweepBudget;   // max velocity sweeps a solve may need to converge (>= 180: unlimited)
@@ -1283,6 +1286,100 @@ HK_HD void bodyAdvance(const Scene& S, Body& b, int bi, float alpha) {  // b2Bod
   b.p = b.c - mul(b.q, s.lc);
 }
 
+// Exact proof that b2TimeOfImpact cannot answer "touching" for static fixture fA vs body bi over this tick's sweep
+// (see the comment at its use in solveTOI).  Only valid before any TOI event, with the body's sweep start being the
+// pose Collide saw (the body went through this tick's island solve) and alpha0 == 0.
+HK_HD bool toiProvablySeparated(const Scene& S, const Env& e, int pid, int fA, int bi, float radiusB) {
+  const Body& B = e.b[bi];
+  V2 dc = B.c - B.c0;
+  float toward = -dot(e.sepNormal[pid], dc);
+  float disp = fmax2(toward, 0.0f) + (bi == B_PUCK ? 0.0f : 0.5f * fabs2(B.a - B.a0));
+  float totalRadius = HK_POLYGON_RADIUS + radiusB;
+  float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
+  if (e.sepBound[pid] - disp > target + 0.25f * HK_LINEAR_SLOP + 0.002f) return true;
+  // second proof (same as the fast tier): the swept core AABB of the body stays clear of the static core AABB
+  float da = fabs2(B.a - B.a0);
+  if (bi != B_PUCK && da > 0.2f) return false;
+  float sag = bi == B_PUCK ? 0.0f : 0.0625f * da * da;
+  AABB st = S.sfat[fA];
+  const float d = HK_AABB_EXTENSION + HK_POLYGON_RADIUS;
+  st.lx += d; st.ly += d; st.hx -= d; st.hy -= d;
+  AABB mv = e.swept[bi];
+  mv.lx += radiusB; mv.ly += radiusB; mv.hx -= radiusB; mv.hy -= radiusB;
+  float gx = fmax2(st.lx - mv.hx, mv.lx - st.hx), gy = fmax2(st.ly - mv.hy, mv.ly - st.hy);
+  return fmax2(gx, gy) > target + 0.25f * HK_LINEAR_SLOP + sag + 0.005f;
+}
+
+// One first-pass TOI evaluation as a self-contained task (hk_lib.cu runs these block-wide, one task per thread,
+// so that the lanes of a warp sit in b2TimeOfImpact together instead of one after the other).
+struct ToiTask {
+  V2 c0, c;
+  float a0, a;
+  int pid;
+};
+HK_HD float toiTaskRun(const Scene& S, const ToiTask& t) {
+  const int fA = S.pairFA[t.pid], fB = S.pairFB[t.pid];
+  const int bi = fB - F_R1;
+  Proxy pA, pB;
+  pA.poly = &S.poly[fA];
+  pA.radius = HK_POLYGON_RADIUS;
+  if (fB == F_PUCK) {
+    pB.poly = nullptr;
+    pB.radius = S.puckRadius;
+  } else {
+    pB.poly = &S.poly[fB];
+    pB.radius = HK_POLYGON_RADIUS;
+  }
+  Sweep sA;
+  sA.lc = mk(0.0f, 0.0f);
+  sA.c0 = sA.c = mk(S.spx[fA], S.spy[fA]);
+  sA.a0 = sA.a = 0.0f;
+  sA.alpha0 = 0.0f;
+  sA.rot = false;
+  Sweep sB;
+  sB.lc = mk(S.lcx[bi], S.lcy[bi]);
+  sB.c0 = t.c0;
+  sB.c = t.c;
+  sB.a0 = t.a0;
+  sB.a = t.a;
+  sB.alpha0 = 0.0f;
+  sB.rot = bi != B_PUCK;
+  int state;
+  float tt;
+  timeOfImpact(&state, &tt, pA, sA, pB, sB, 1.0f);
+  const float alpha0 = 0.0f;
+  return state == TOI_TOUCHING ? fmin2(alpha0 + (1.0f - alpha0) * tt, 1.0f) : 1.0f;
+}
+// First pass of b2World::SolveTOI's candidate loop for one env: pairs that the proofs settle get alpha = 1 right
+// away, the others become tasks (up to maxTasks; the rest is left to solveTOI itself).  Returns the task count.
+HK_HD int toiCollect(const Scene& S, Env& e, ToiTask* tasks, int maxTasks) {
+  e.toiPreFlag = 0;
+  int nt = 0;
+  const uint32_t solvedMask = (e.b[0].island ? 1u : 0u) | (e.b[1].island ? 2u : 0u) | (e.b[2].island ? 4u : 0u);
+  for (int i = 0; i < e.ncontacts; ++i) {
+    int pid = clistGet(e.clist, i);
+    uint32_t bit = 1u << pid;
+    if (!(e.enabled & bit) || !(HK_PAIRS_TOI & bit)) continue;
+    int fA = S.pairFA[pid], fB = S.pairFB[pid];
+    int bi = fB - F_R1;
+    const Body& B = e.b[bi];
+    if (!B.awake) continue;
+    float rB = fB == F_PUCK ? S.puckRadius : HK_POLYGON_RADIUS;
+    if (((solvedMask >> bi) & 1u) && toiProvablySeparated(S, e, pid, fA, bi, rB)) {
+      e.toiPre[pid] = 1.0f;
+      e.toiPreFlag |= bit;
+    } else if (nt < maxTasks) {
+      ToiTask& t = tasks[nt++];
+      t.c0 = B.c0;
+      t.c = B.c;
+      t.a0 = B.a0;
+      t.a = B.a;
+      t.pid = pid;
+    }
+  }
+  return nt;
+}
+
 HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float dt, int velIters) {
   HK_TOI_DBG(10);
   float salpha[8];  // alpha0 of the 8 static bodies (statics are immovable: only alpha0 advances)
@@ -1291,13 +1388,14 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
   const uint32_t solvedMask = (e.b[0].island ? 1u : 0u) | (e.b[1].island ? 2u : 0u) | (e.b[2].island ? 4u : 0u);
   e.b[0].island = e.b[1].island = e.b[2].island = false;
   e.b[0].alpha0 = e.b[1].alpha0 = e.b[2].alpha0 = 0.0f;
-  uint32_t toiFlag = 0;
+  uint32_t toiFlag = e.toiPreFlag;  // first-pass results computed ahead by the block-wide task pass (or 0)
   float toi[N_PAIRS];
   unsigned char toiCount[N_PAIRS];
   for (int i = 0; i < N_PAIRS; ++i) {
-    toi[i] = 1.0f;
+    toi[i] = ((toiFlag >> i) & 1u) ? e.toiPre[i] : 1.0f;
     toiCount[i] = 0;
   }
+  e.toiPreFlag = 0;
   for (;;) {
     int minPid = -1;
     float minAlpha = 1.0f;
@@ -1353,37 +1451,21 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
         // along that face normal n no point of the body approaches the plane by more than max(0, -n.dc) + R |da|
         // (linear centre motion, |r| <= R = 0.5 m from the centre of mass).  If what remains stays above
         // target + tolerance (+ margin) the answer is alpha = 1.
-        bool skip = false;
-        if (!e.toiEventSeen && alpha0 == 0.0f && ((solvedMask >> bi) & 1u)) {
-          V2 dc = B.c - B.c0;
-          float toward = -dot(e.sepNormal[pid], dc);
-          float disp = fmax2(toward, 0.0f) + (bi == B_PUCK ? 0.0f : 0.5f * fabs2(B.a - B.a0));
-          float totalRadius = pA.radius + pB.radius;
-          float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
-          skip = e.sepBound[pid] - disp > target + 0.25f * HK_LINEAR_SLOP + 0.002f;
-          if (!skip) {
-            // second proof (same as the fast tier): the swept core AABB of the body stays clear of the static core AABB
-            float r = pB.radius;
-            float da = fabs2(B.a - B.a0);
-            if (bi == B_PUCK || da <= 0.2f) {
-              float sag = bi == B_PUCK ? 0.0f : 0.0625f * da * da;
-              AABB st = S.sfat[fA];
-              const float d = HK_AABB_EXTENSION + HK_POLYGON_RADIUS;
-              st.lx += d; st.ly += d; st.hx -= d; st.hy -= d;
-              AABB mv = e.swept[bi];
-              mv.lx += r; mv.ly += r; mv.hx -= r; mv.hy -= r;
-              float gx = fmax2(st.lx - mv.hx, mv.lx - st.hx), gy = fmax2(st.ly - mv.hy, mv.ly - st.hy);
-              skip = fmax2(gx, gy) > target + 0.25f * HK_LINEAR_SLOP + sag + 0.005f;
-            }
-          }
-        }
+        bool skip = !e.toiEventSeen && alpha0 == 0.0f && ((solvedMask >> bi) & 1u) &&
+                    toiProvablySeparated(S, e, pid, fA, bi, pB.radius);
         HK_TOI_DBG(bi == B_PUCK ? 0 : 1);
         if (skip) {
           state = TOI_SEPARATED;
           t = 1.0f;
           HK_TOI_DBG(bi == B_PUCK ? 2 : 3);
         } else {
+#if defined(__CUDA_ARCH__)
+          long long c0_ = clock64();
+#endif
           timeOfImpact(&state, &t, pA, sA, pB, sB, 1.0f);
+#if defined(__CUDA_ARCH__)
+          e.dbgEvalClk += clock64() - c0_;
+#endif
           HK_TOI_DBG(bi == B_PUCK ? 4 : 5);
           if (e.toiEventSeen) HK_TOI_DBG(6);
           else if (!(alpha0 == 0.0f && ((solvedMask >> bi) & 1u))) HK_TOI_DBG(7);
@@ -1408,6 +1490,9 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
     }
     e.nToiEvents++;
     e.toiEventSeen = true;
+#if defined(__CUDA_ARCH__)
+    long long ev0_ = clock64();
+#endif
 
     const int fA = S.pairFA[minPid], fB = S.pairFB[minPid];
     const int bi = fB - F_R1;
@@ -1492,6 +1577,9 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
     synchronizeFixtures(S, e, bi);
     toiFlag &= ~mine;
     findNewContacts(S, e);
+#if defined(__CUDA_ARCH__)
+    e.dbgEventClk += clock64() - ev0_;
+#endif
   }
 }
 
@@ -1502,6 +1590,7 @@ HK_HD_NOINLINE void worldStepCollide(const Scene& S, const Config& cfg, const Ca
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   e.toiEventSeen = false;
+  e.toiPreFlag = 0;
   for (int k = 0; k < N_PAIRS; ++k) e.sepBound[k] = -HK_MAXFLOAT;
   if (e.moved & 8u) {
     e.moved &= ~8u;

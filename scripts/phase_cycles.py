@@ -17,3 +17,5 @@ v = list(out)
 for t in range(2):
     tot = sum(v[4 * t:4 * t + 4]) or 1.0
     print(f"tier {t + 1}: " + "  ".join(f"{name} {100 * v[4 * t + k] / tot:5.1f}%" for k, name in enumerate(("policy+collide", "island-solve", "TOI", "finish"))), f" total {tot:.3g} block-cycles")
+tot1 = sum(v[0:4]) or 1.0
+print(f"tier-1 TOI phase split (block max of per-lane cycles, tiers=2 only): evaluation calls {100 * v[4] / tot1:.1f}% of tier time, event handling {100 * v[5] / tot1:.1f}%")

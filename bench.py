@@ -97,7 +97,7 @@ def run_reference(args, rank, world):
     sys.path.insert(0, os.path.join(_ROOT, "tests"))
     import oracle_lib as O
     cores = os.cpu_count() or 1
-    n = 256 * cores  # bounded sample of the 65,536-env workload
+    n = 1024 * cores  # bounded sample of the 65,536-env workload (large enough to amortise the per-tick thread start)
     b = O.OracleBatch(n, mode=O.MODE_NORMAL, seed=args.seed, n_threads=cores)
     import numpy as np
     b.reset(one_starting=(np.arange(n) % 2).astype(np.int8))

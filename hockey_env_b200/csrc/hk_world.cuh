@@ -618,9 +618,8 @@ HK_HD_NOINLINE void warmStartConstraint(Env& e, const VC& vc) {
 }
 
 // one Gauss-Seidel pass over one contact; returns true if any applied impulse increment was non-zero
-HK_HD_NOINLINE bool solveVelocityConstraint(Env& e, VC& vc) {
+HK_HD bool solveVelocityConstraintCore(VC& vc, Vel& A, Vel& B) {
   bool changed = false;
-  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   V2 vA = A.v, vB = B.v;
   float wA = A.w, wB = B.w;
@@ -709,6 +708,11 @@ HK_HD_NOINLINE bool solveVelocityConstraint(Env& e, VC& vc) {
   A.w = wA;
   B.v = vB;
   B.w = wB;
+  return changed;
+}
+HK_HD_NOINLINE bool solveVelocityConstraint(Env& e, VC& vc) {
+  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
+  bool changed = solveVelocityConstraintCore(vc, A, B);
   storeVel(e, vc.bA, A);
   storeVel(e, vc.bB, B);
   return changed;
@@ -739,10 +743,11 @@ HK_HD_NOINLINE void snapSave(const Env& e, const VC* vcs, int nvc, SolveSnap& s)
   }
 }
 HK_HD_NOINLINE bool snapEqual(const SolveSnap& a, const SolveSnap& b, int nvc) {
-  bool eq = true;
-  for (int i = 0; i < 9; ++i) eq = eq && (a.v[i] == b.v[i]);
-  for (int i = 0; i < 4 * nvc; ++i) eq = eq && (a.imp[i] == b.imp[i]);
-  return eq;
+  for (int i = 0; i < 4 * nvc; ++i)  // impulses first: they are what still moves when the velocities have settled
+    if (!(a.imp[i] == b.imp[i])) return false;
+  for (int i = 0; i < 9; ++i)
+    if (!(a.v[i] == b.v[i])) return false;
+  return true;
 }
 HK_HD_NOINLINE void snapRestore(Env& e, VC* vcs, int nvc, const SolveSnap& s) {
   for (int b = 0; b < 3; ++b) {
@@ -969,32 +974,54 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
 HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
   if (nvc == 1 && vcs[0].count == 1) return runVelocityIterations1(e, vcs[0], velIters);
   if (nvc == 1 && vcs[0].count == 2) return runVelocityIterations2(e, vcs[0], velIters);
-  SolveSnap p1, p2;  // states after the previous sweep and the one before
+  SolveSnap snaps[3];  // rotating: [it % 3] = state after sweep it (so (it-1) % 3 and (it-2) % 3 are the two before)
   const int kFirstSnap = 2;
+  // the three bodies' velocities stay in registers for the whole loop (selected by index, no local-memory round trips)
+  Vel v0 = loadVel(e, 0), v1 = loadVel(e, 1), v2 = loadVel(e, 2);
+  Vel zero;
+  zero.v = mk(0.0f, 0.0f);
+  zero.w = 0.0f;
   int it = 0;
+  int result = 0;
   for (; it < velIters; ++it) {
     bool changed = false;
-    for (int k = 0; k < nvc; ++k) changed = solveVelocityConstraint(e, vcs[k]) || changed;
-    e.nVelIters++;
-    if (!changed) {
-      ++it;
-      break;
+    for (int k = 0; k < nvc; ++k) {
+      const int bA = vcs[k].bA, bB = vcs[k].bB;
+      Vel A = bA == 0 ? v0 : (bA == 1 ? v1 : (bA == 2 ? v2 : zero));
+      Vel B = bB == 0 ? v0 : (bB == 1 ? v1 : (bB == 2 ? v2 : zero));
+      changed = solveVelocityConstraintCore(vcs[k], A, B) || changed;
+      if (bA == 0) v0 = A; else if (bA == 1) v1 = A; else if (bA == 2) v2 = A;
+      if (bB == 0) v0 = B; else if (bB == 1) v1 = B; else if (bB == 2) v2 = B;
     }
+    e.nVelIters++;
+    result = it + 1;
+    if (!changed) break;
     if (it >= kFirstSnap) {
-      SolveSnap cur;
+      SolveSnap& cur = snaps[it % 3];
+      storeVel(e, 0, v0);
+      storeVel(e, 1, v1);
+      storeVel(e, 2, v2);
       snapSave(e, vcs, nvc, cur);
-      if (it >= kFirstSnap + 2 && snapEqual(cur, p2, nvc)) {
+      if (it >= kFirstSnap + 2 && snapEqual(cur, snaps[(it + 1) % 3], nvc)) {  // (it - 2) % 3 == (it + 1) % 3
         const int remaining = velIters - 1 - it;
-        if (remaining & 1) snapRestore(e, vcs, nvc, p1);
-        ++it;
+        if (remaining & 1) {
+          snapRestore(e, vcs, nvc, snaps[(it + 2) % 3]);                         // (it - 1) % 3
+          v0 = loadVel(e, 0);
+          v1 = loadVel(e, 1);
+          v2 = loadVel(e, 2);
+        }
         break;
       }
-      p2 = p1;
-      p1 = cur;
     }
-    if (it + 1 >= e.sweepBudget && it + 1 < velIters) return -1;
+    if (it + 1 >= e.sweepBudget && it + 1 < velIters) {
+      result = -1;
+      break;
+    }
   }
-  return it;
+  storeVel(e, 0, v0);
+  storeVel(e, 1, v1);
+  storeVel(e, 2, v2);
+  return result;
 }
 
 // b2ContactSolver::SolvePositionConstraints / SolveTOIPositionConstraints for one contact.

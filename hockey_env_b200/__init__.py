@@ -11,5 +11,8 @@ from .env import (  # noqa: F401
     RACKETPOLY, RACKETFACTOR, FORCEMULTIPLIER, SHOOTFORCEMULTIPLIER, TORQUEMULTIPLIER, MAX_PUCK_SPEED,
 )
 
-__all__ = ["HockeyVecEnv", "HockeyEnv", "HockeyEnv_BasicOpponent", "BasicOpponent", "PolicyOpponent", "Mode",
+from .vector import HockeyGymVectorEnv  # noqa: F401
+from .actor import ActorNetwork, actor_rollout, load_td3_actor  # noqa: F401
+
+__all__ = ["HockeyGymVectorEnv", "ActorNetwork", "actor_rollout", "load_td3_actor", "HockeyVecEnv", "HockeyEnv", "HockeyEnv_BasicOpponent", "BasicOpponent", "PolicyOpponent", "Mode",
            "HockeyLibraryError", "load_library"]

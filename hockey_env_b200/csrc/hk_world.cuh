@@ -766,6 +766,8 @@ HK_HD_NOINLINE void snapRestore(Env& e, VC* vcs, int nvc, const SolveSnap& s) {
 // Specialised sweep loop for the dominant case -- one contact with one manifold point (95 % of solves): every
 // quantity lives in registers, same expression order as solveVelocityConstraint().
 HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
+  const int budget = e.sweepBudget;  // keep the loop free of accesses through e (local memory)
+  int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   const V2 normal = vc.normal;
   const V2 tangent = cross(normal, 1.0f);
@@ -812,7 +814,7 @@ HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
       vB += mB * P;
       wB += iB * cross(rB, P);
     }
-    e.nVelIters++;
+    ++sweeps;
     if (!changed) {
       result = it + 1;
       break;
@@ -829,7 +831,7 @@ HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
     }
     vA2 = vA1; vB2 = vB1; wA2 = wA1; wB2 = wB1; ni2 = ni1; ti2 = ti1;
     vA1 = vA; vB1 = vB; wA1 = wA; wB1 = wB; ni1 = ni; ti1 = ti;
-    if (it + 1 >= e.sweepBudget && it + 1 < velIters) {
+    if (it + 1 >= budget && it + 1 < velIters) {
       result = -1;
       break;
     }
@@ -840,12 +842,15 @@ HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
   A.v = vA; A.w = wA; B.v = vB; B.w = wB;
   storeVel(e, vc.bA, A);
   storeVel(e, vc.bB, B);
+  e.nVelIters += (uint32_t)sweeps;
   return result;
 }
 
 // Same for one contact with a two-point manifold (racket resting on a wall / goal): tangent rows, then the 2x2
 // block solver of b2ContactSolver::SolveVelocityConstraints, all in registers.
 HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
+  const int budget = e.sweepBudget;  // keep the loop free of accesses through e (local memory)
+  int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   const V2 normal = vc.normal;
   const V2 tangent = cross(normal, 1.0f);
@@ -941,7 +946,7 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
         changed = changed || (d.x != 0.0f) || (d.y != 0.0f);
       }
     }
-    e.nVelIters++;
+    ++sweeps;
     result = it + 1;
     if (!changed) break;
     if (it >= 2 && vA.x == vAq.x && vA.y == vAq.y && wA == wAq && vB.x == vBq.x && vB.y == vBq.y && wB == wBq &&
@@ -954,7 +959,7 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
     }
     vAq = vAp; vBq = vBp; wAq = wAp; wBq = wBp; ni0q = ni0p; ti0q = ti0p; ni1q = ni1p; ti1q = ti1p;
     vAp = vA; vBp = vB; wAp = wA; wBp = wB; ni0p = ni0; ti0p = ti0; ni1p = ni1; ti1p = ti1;
-    if (it + 1 >= e.sweepBudget && it + 1 < velIters) {
+    if (it + 1 >= budget && it + 1 < velIters) {
       result = -1;
       break;
     }
@@ -966,6 +971,7 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
   A.v = vA; A.w = wA; B.v = vB; B.w = wB;
   storeVel(e, vc.bA, A);
   storeVel(e, vc.bB, B);
+  e.nVelIters += (uint32_t)sweeps;
   return result;
 }
 
@@ -974,6 +980,8 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
 HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
   if (nvc == 1 && vcs[0].count == 1) return runVelocityIterations1(e, vcs[0], velIters);
   if (nvc == 1 && vcs[0].count == 2) return runVelocityIterations2(e, vcs[0], velIters);
+  const int budget = e.sweepBudget;
+  int sweeps = 0;
   SolveSnap snaps[3];  // rotating: [it % 3] = state after sweep it (so (it-1) % 3 and (it-2) % 3 are the two before)
   const int kFirstSnap = 2;
   // the three bodies' velocities stay in registers for the whole loop (selected by index, no local-memory round trips)
@@ -993,7 +1001,7 @@ HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters)
       if (bA == 0) v0 = A; else if (bA == 1) v1 = A; else if (bA == 2) v2 = A;
       if (bB == 0) v0 = B; else if (bB == 1) v1 = B; else if (bB == 2) v2 = B;
     }
-    e.nVelIters++;
+    ++sweeps;
     result = it + 1;
     if (!changed) break;
     if (it >= kFirstSnap) {
@@ -1013,7 +1021,7 @@ HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters)
         break;
       }
     }
-    if (it + 1 >= e.sweepBudget && it + 1 < velIters) {
+    if (it + 1 >= budget && it + 1 < velIters) {
       result = -1;
       break;
     }
@@ -1021,6 +1029,7 @@ HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters)
   storeVel(e, 0, v0);
   storeVel(e, 1, v1);
   storeVel(e, 2, v2);
+  e.nVelIters += (uint32_t)sweeps;
   return result;
 }
 

@@ -28,8 +28,8 @@ ENVS_PER_GPU = 65536
 # written + obs 72 + reward 4 + done 1 + info 16 (in-kernel opponents: no action read)
 ALGO_BYTES_PER_ENV_STEP = 256 + 256 + 72 + 4 + 1 + 16
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_general<1>) for one launch at 65,536 envs, from the
-# `ncu --set full` capture summarised in profiles/r1_final_raw_metrics.csv (48.0 MB read + 53.0 MB written)
-NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 = 100_974_848
+# `ncu --set full` capture summarised in profiles/r1_final_raw_metrics.csv (47.7 MB read + 50.8 MB written)
+NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 = 98_568_448
 
 
 def _peaks():

@@ -316,6 +316,16 @@ HK_HD_NOINLINE void policyActions(const Config& cfg, Env& e, uint64_t env_id, co
   }
 }
 
+// the state side effect of policyActions (BasicOpponent.phase += U(0, 0.2), hockey_env.py:796) without the controller
+// arithmetic: used when the actions of this tick were already computed by the fast tier
+HK_HD void policyAdvancePhases(const Config& cfg, Env& e, uint64_t env_id, int pol1, int pol2) {
+  if (pol1 == 1 || pol1 == 2 || pol2 == 1 || pol2 == 2) {
+    U4 ro = philox(cfg.seed, env_id, e.tick, HK_STREAM_OPP);
+    if (pol1 == 1 || pol1 == 2) e.phase[0] += 0.0 + (0.2 - 0.0) * u53(ro.x, ro.y);
+    if (pol2 == 1 || pol2 == 2) e.phase[1] += 0.0 + (0.2 - 0.0) * u53(ro.z, ro.w);
+  }
+}
+
 // step (hockey_env.py:658-695) with an already clipped float32 action; everything before world.Step
 HK_HD_NOINLINE void envStepActions(const Scene& S, const Config& cfg, Env& e, const float action[8]) {
   Body &p1 = e.b[B_R1], &p2 = e.b[B_R2], &puck = e.b[B_PUCK];

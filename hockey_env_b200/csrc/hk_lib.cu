@@ -111,6 +111,7 @@ struct KParams {
   int32_t* queue;    // [5][n] env indices queued for the general tiers this tick, see Q_* below
   uint32_t* qctl;    // queue counters, see Q_* below
   unsigned long long* phaseClk;  // [2 tiers][4 phases] block-cycles spent per phase (diagnostics, hk_debug_phase_cycles)
+  float* actBuf;     // [n,8] actions handed from k_fast to the general tiers
   int64_t n;
   int64_t env_id_offset;
   Config cfg;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
     Env e;
     loadEnv(P.core, P.n, i, e);
     e.bailKind = 15;
-    ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st);
+    ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st);
     if (ok) storeEnv(P.core, P.n, i, e);
     else {
       tickStatsZero(st);
@@ -267,7 +268,14 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   if (valid) {  // phase 1: policy, forces, keep/shoot, Collide
     loadEnv(P.core, P.n, i, e);
     float a[8];
-    policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+    if (io.actBuf) {  // k_fast already ran the controllers for this tick
+      const float4* ab = reinterpret_cast<const float4*>(io.actBuf + 8 * i);
+      float4 lo = ab[0], hi = ab[1];
+      a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+      policyAdvancePhases(P.cfg, e, env_id, io.pol1, io.pol2);
+    } else {
+      policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+    }
     had1 = e.has1;
     had2 = e.has2;
     e.sweepBudget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
@@ -329,7 +337,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     if (!e.aborted) {
       worldStepFinish(cache, e);
       envStepAfterWorld(P.cfg, e);
-      tickFinish(S, P.cfg, e, env_id, (size_t)i, io, true, st, had1, had2);
+      tickFinish(S, P.cfg, e, env_id, (size_t)i, io, io.write != 0, st, had1, had2);
       storeEnv(P.core, P.n, i, e);
     } else {
       need = true;
@@ -471,6 +479,7 @@ struct hk_env {
   int32_t* queue;
   uint32_t* qctl;
   unsigned long long* phaseClk;
+  float* actBuf;
   int tiers;  // HK_TIERS=2: fast + unlimited general tier; 3 (default): fast + budgeted + unlimited
   bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
@@ -481,6 +490,7 @@ struct hk_env {
     P.queue = queue;
     P.qctl = qctl;
     P.phaseClk = phaseClk;
+    P.actBuf = actBuf;
     P.n = n;
     P.env_id_offset = env_id_offset;
     P.cfg = cfg;
@@ -539,6 +549,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   h->queue = nullptr;
   h->qctl = nullptr;
   h->phaseClk = nullptr;
+  h->actBuf = nullptr;
   {
     const char* m = getenv("HK_MONO");
     h->mono = m && m[0] == '1';
@@ -564,6 +575,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * 5 * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 8);
+  if (err == cudaSuccess) err = cudaMalloc(&h->actBuf, sizeof(float) * 8 * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->phaseClk, sizeof(unsigned long long) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
@@ -581,6 +593,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     cudaFree(h->queue);
     cudaFree(h->qctl);
     cudaFree(h->phaseClk);
+    cudaFree(h->actBuf);
     delete h;
     return fail(HK_E_CUDA, msg);
   }
@@ -597,6 +610,7 @@ int hk_destroy(hk_env* h) {
   cudaFree(h->queue);
   cudaFree(h->qctl);
   cudaFree(h->phaseClk);
+  cudaFree(h->actBuf);
   delete h;
   return HK_OK;
 }
@@ -637,9 +651,12 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
   io.info = info_dev;
   io.info2 = info2_dev;
   io.final_obs = final_obs_dev;
+  io.write = 1;
+  io.actBuf = nullptr;
   if (h->mono) {
     k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
   } else {
+    io.actBuf = h->actBuf;
     k_fast<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
     const int b1 = h->blockFor(0.5), b2 = h->blockFor(0.1);
     k_general<1><<<h->gridSlow(h->lanes1, b1), b1, 0, (cudaStream_t)stream>>>(h->params(), io, h->tiers == 2 ? 1 : 0, h->lanes1);
@@ -662,7 +679,20 @@ int hk_rollout(hk_env* h, int k_steps, int p1_policy, int p2_policy, float* obs_
   io.pol2 = p2_policy;
   io.flags = HK_STEP_AUTORESET;
   io.obs = obs_dev;
-  k_rollout<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io, k_steps);
+  if (h->mono) {  // K ticks fused in one launch, state in registers between ticks (the round-1 baseline kernel)
+    io.write = 1;
+    k_rollout<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io, k_steps);
+  } else {        // K ticks of the kernel cascade back to back; only the last tick writes its observation
+    io.actBuf = h->actBuf;
+    const int b1 = h->blockFor(0.5), b2 = h->blockFor(0.1);
+    for (int s = 0; s < k_steps; ++s) {
+      io.write = (s == k_steps - 1 && obs_dev) ? 1 : 0;
+      k_fast<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
+      k_general<1><<<h->gridSlow(h->lanes1, b1), b1, 0, (cudaStream_t)stream>>>(h->params(), io, h->tiers == 2 ? 1 : 0, h->lanes1);
+      if (h->tiers == 3)
+        k_general<2><<<h->gridSlow(h->lanes2, b2), b2, 0, (cudaStream_t)stream>>>(h->params(), io, 1, h->lanes2);
+    }
+  }
   HK_CUDA(cudaGetLastError());
   return HK_OK;
 }

@@ -19,6 +19,8 @@ struct StepIO {
   float* info;       // [n,4] or null
   float* info2;      // [n,4] or null
   float* final_obs;  // [n,18] or null
+  int write;         // 0: suppress all per-tick outputs (inner ticks of hk_rollout)
+  float* actBuf;     // [n,8] scratch: clipped actions k_fast computed for the envs it hands to the general tiers
 };
 
 struct TickStats {
@@ -125,7 +127,12 @@ HK_HD bool envTickFast(const Scene& S, const Config& cfg, Env& e, uint64_t env_i
   float a[8];
   policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
   const int had1 = e.has1, had2 = e.has2;
-  if (!envStepFast(S, cfg, e, a)) return false;
+  if (!envStepFast(S, cfg, e, a)) {
+    if (io.actBuf) {  // the general tier redoes the tick from the stored state; spare it the controllers
+      for (int k = 0; k < 8; ++k) io.actBuf[8 * i + k] = a[k];
+    }
+    return false;
+  }
   tickFinish(S, cfg, e, env_id, i, io, write, st, had1, had2);
   return true;
 }

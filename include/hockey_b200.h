@@ -120,9 +120,10 @@ int hk_step(hk_env* env, const float* action_dev, int action_stride, int p1_poli
             float* obs_dev, float* obs2_dev, float* reward_dev, float* reward2_dev, uint8_t* done_dev,
             float* info_dev, float* info2_dev, float* final_obs_dev, void* stream);
 
-/* k_steps fused ticks in ONE launch with in-kernel policies (no EXTERNAL), autoreset on; body
- * state stays in registers between ticks.  Only the last tick's obs (nullable) is written; episode
- * statistics accumulate in the handle (hk_get_stats). */
+/* k_steps ticks with in-kernel policies (no EXTERNAL), autoreset on, enqueued back to back without any
+ * per-tick output: only the last tick's obs (nullable) is written; episode statistics accumulate in
+ * the handle (hk_get_stats).  (With HK_MONO=1 the k_steps ticks are fused into ONE launch with the
+ * body state held in registers between ticks.) */
 int hk_rollout(hk_env* env, int k_steps, int p1_policy, int p2_policy, float* obs_dev, void* stream);
 
 /* Observations of the current state without stepping (_get_obs / obs_agent_two, hockey_env.py:485-516). */

@@ -189,6 +189,10 @@ HK_HD_NOINLINE void collidePolygons(Manifold* m, const Poly& polyA, const Xf& xf
   if (separationA > totalRadius) return;
   int edgeB = 0;
   float separationB = findMaxSeparation(&edgeB, polyB, xfB, polyA, xfA);
+  if (separationB > m->sepBound) {  // a face separation of B bounds the distance as well, but its normal moves with B
+    m->sepBound = separationB;
+    m->sepNormal = mk(0.0f, 0.0f);
+  }
   if (separationB > totalRadius) return;
   const float k_relativeTol = 0.98f;
   const float k_absoluteTol = 0.001f;

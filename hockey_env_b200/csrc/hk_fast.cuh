@@ -51,20 +51,31 @@ HK_HD float aabbGap(const AABB& a, const AABB& b) {
   float gy = fmax2(a.ly - b.hy, b.ly - a.hy);
   return fmax2(gx, gy);
 }
-// gap restricted to the face normals the static polygon really has (+-x always; +-y for boxes f<2, f>=6;
-// corner trapezoids: only the outward y face: -y for bottom ones (3,5), +y for top ones (2,4))
-HK_HD float staticFaceGap(int f, const AABB& a /*static core*/, const AABB& b /*moving core*/) {
-  float g = fmax2(b.lx - a.hx, a.lx - b.hx);
-  bool hasUp = f < 2 || f >= 6 || f == 2 || f == 4;
-  bool hasDown = f < 2 || f >= 6 || f == 3 || f == 5;
-  if (hasUp) g = fmax2(g, b.ly - a.hy);
-  if (hasDown) g = fmax2(g, a.ly - b.hy);
-  return g;
+// Largest separation of the racket's vertices from a face plane of static polygon f (statics have angle 0).  The
+// static polygons have four faces; b2FindMaxSeparation's hill climb (2.3.0) starts at the face best aligned with
+// the centroid direction, examines it and both neighbours and keeps the largest, and the start face cannot be the
+// one opposite a face that separates the shapes -- so whenever this value exceeds totalRadius the climb returns a
+// separation above totalRadius as well and b2CollidePolygons produces no manifold points.
+HK_HD float polyStaticFaceGap(const Scene& S, int f, const Poly& PB, const Xf& xfB, V2* normal) {
+  const Poly& PA = S.poly[f];
+  const float ox = S.spx[f], oy = S.spy[f];
+  float s0 = HK_MAXFLOAT, s1 = HK_MAXFLOAT, s2 = HK_MAXFLOAT, s3 = HK_MAXFLOAT;
+  for (int i = 0; i < PB.count; ++i) {
+    V2 v = mul(xfB, polyV(PB, i));
+    const float x = v.x - ox, y = v.y - oy;
+    s0 = fmin2(s0, PA.nx[0] * (x - PA.vx[0]) + PA.ny[0] * (y - PA.vy[0]));
+    s1 = fmin2(s1, PA.nx[1] * (x - PA.vx[1]) + PA.ny[1] * (y - PA.vy[1]));
+    s2 = fmin2(s2, PA.nx[2] * (x - PA.vx[2]) + PA.ny[2] * (y - PA.vy[2]));
+    s3 = fmin2(s3, PA.nx[3] * (x - PA.vx[3]) + PA.ny[3] * (y - PA.vy[3]));
+  }
+  int k = 0;
+  float best = s0;
+  if (s1 > best) { best = s1; k = 1; }
+  if (s2 > best) { best = s2; k = 2; }
+  if (s3 > best) { best = s3; k = 3; }
+  *normal = polyN(PA, k);
+  return best;
 }
-
-struct FastScratch {
-  AABB swept[3];  // tight swept AABB (with shape radius) from this tick's synchronizeFixtures
-};
 
 HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, Env& e) {
   int i = 0;
@@ -104,17 +115,31 @@ HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, Env& e) {
       Manifold m;
       collidePolygonCircle(&m, S.poly[fA], fixtureXf(S, e, fA), e.b[B_PUCK].p, S.puckRadius);
       if (m.count > 0) HK_BAIL(3 + (fA >= F_R1 ? 1 : 0));
+      e.sepBound[pid] = m.sepBound;
+      e.sepNormal[pid] = m.sepNormal;
       touching = false;
     } else {
       if (bA >= 0) HK_BAIL(5);  // racket x racket: general path
-      AABB a = staticCoreAABB(S, fA);
-      AABB b = shapeAABB(S, bB, bodyXf(e.b[bB]));
-      b.lx += HK_POLYGON_RADIUS;
-      b.ly += HK_POLYGON_RADIUS;
-      b.hx -= HK_POLYGON_RADIUS;
-      b.hy -= HK_POLYGON_RADIUS;
-      if (staticFaceGap(fA, a, b) > 2.0f * HK_POLYGON_RADIUS + HK_FAST_EPS) touching = false;
-      else HK_BAIL(6);
+      // the face separation doubles as the distance bound of the TOI proof (toiProvablySeparated); 0.001 covers the
+      // rounding of this evaluation order against the one a real face separation would have
+      V2 nrm;
+      const float gap = polyStaticFaceGap(S, fA, S.poly[fB], bodyXf(e.b[bB]), &nrm);
+      e.sepBound[pid] = gap - 0.001f;
+      e.sepNormal[pid] = nrm;
+      if (gap > 2.0f * HK_POLYGON_RADIUS + 0.0005f) {
+        touching = false;
+      } else {
+        // corner against corner: a racket face may separate the shapes.  This is b2CollidePolygons' own second
+        // search (same function, same arguments): above totalRadius it returns without manifold points.
+        int edgeB = 0;
+        const float sB = findMaxSeparation(&edgeB, S.poly[fB], bodyXf(e.b[bB]), S.poly[fA], staticXf(S, fA));
+        if (!(sB > 2.0f * HK_POLYGON_RADIUS)) HK_BAIL(6);
+        touching = false;
+        if (sB - 0.001f > e.sepBound[pid]) {  // distance bound without a fixed direction (the racket's face turns with it)
+          e.sepBound[pid] = sB - 0.001f;
+          e.sepNormal[pid] = mk(0.0f, 0.0f);
+        }
+      }
     }
     if (!(HK_PAIRS_SENSOR & bit)) {
       setCount(e, pid, 0);
@@ -150,13 +175,13 @@ HK_HD_NOINLINE void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot 
 HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float h) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
+  for (int k = 0; k < N_PAIRS; ++k) e.sepBound[k] = -HK_MAXFLOAT;
   if (e.moved & 8u) {
     e.moved &= ~8u;
     findNewContacts(S, e);
   }
   if (!collideFast(S, cfg, e)) return false;  // bailKind set by collideFast
   // ---- b2World::Solve with no constraints: every awake body is its own island ----
-  FastScratch fs;
   Rot q0[3];
   for (int bi = 2; bi >= 0; --bi) {
     Body& b = e.b[bi];
@@ -185,7 +210,7 @@ HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, flo
     if (minSleepTime >= HK_TIME_TO_SLEEP) setAwake(b, false);
   }
   for (int bi = 2; bi >= 0; --bi)
-    if (e.b[bi].island) synchronizeFixturesKeep(S, e, bi, q0[bi], &fs.swept[bi]);
+    if (e.b[bi].island) synchronizeFixturesKeep(S, e, bi, q0[bi], &e.swept[bi]);
   findNewContacts(S, e);
   // ---- b2World::SolveTOI: prove alpha == 1 for every candidate ----
   uint32_t cand = e.exist & HK_PAIRS_TOI;
@@ -198,19 +223,8 @@ HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, flo
       const Body& B = e.b[bi];
       if (!B.awake) continue;
       if (!B.island) HK_BAIL(7);  // woken after the solve (new contact): its sweep is stale, take the general path
-      float r = bi == B_PUCK ? S.puckRadius : HK_POLYGON_RADIUS;
-      AABB mv = fs.swept[bi];
-      mv.lx += r;
-      mv.ly += r;
-      mv.hx -= r;
-      mv.hy -= r;
-      float da = fabs2(B.a - B.a0);
-      if (bi != B_PUCK && da > 0.2f) HK_BAIL(8);
-      float sag = bi == B_PUCK ? 0.0f : 0.0625f * da * da;  // |r| <= 0.5 m from the centre of mass: |r| da^2 / 8
-      float totalRadius = HK_POLYGON_RADIUS + r;
-      float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
-      float need = target + 0.25f * HK_LINEAR_SLOP + sag + HK_FAST_EPS;
-      if (!(aabbGap(staticCoreAABB(S, fA), mv) > need)) HK_BAIL(9 + (bi == B_PUCK ? 1 : 0));
+      const float r = bi == B_PUCK ? S.puckRadius : HK_POLYGON_RADIUS;
+      if (!toiProvablySeparated(S, e, pid, fA, bi, r)) HK_BAIL(9 + (bi == B_PUCK ? 1 : 0));
     }
   }
   for (int bi = 0; bi < 3; ++bi) {

@@ -978,6 +978,27 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
 // general loop: any number of contacts; fixed point and period-2 detection
 // returns the number of sweeps executed, or -1 if the tier's sweep budget ran out before the state repeated
 HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
+#if defined(HK_CYCLE_STUDY) && !defined(__CUDA_ARCH__)
+  {
+    Env e2 = e;
+    VC v2[MAX_MANIFOLDS];
+    for (int k = 0; k < nvc; ++k) v2[k] = vcs[k];
+    static SolveSnap hist[181];
+    for (int it = 0; it < velIters; ++it) {
+      for (int k = 0; k < nvc; ++k) solveVelocityConstraint(e2, v2[k]);
+      memset(&hist[it], 0, sizeof(SolveSnap));
+      snapSave(e2, v2, nvc, hist[it]);
+    }
+    int lam = 0;
+    for (int p = 1; p <= 90; ++p) if (snapEqual(hist[velIters - 1], hist[velIters - 1 - p], nvc)) { lam = p; break; }
+    int mu = -1;
+    if (lam) for (int i = 0; i + lam < velIters; ++i) if (snapEqual(hist[i], hist[i + lam], nvc)) { mu = i; break; }
+    extern long long g_cyc_lam[64], g_cyc_mu[8][182];
+    g_cyc_lam[lam < 63 ? lam : 63]++;
+    int cls = lam == 0 ? 0 : (lam == 1 ? 1 : (lam == 2 ? 2 : (lam <= 4 ? 3 : (lam <= 8 ? 4 : (lam <= 16 ? 5 : 6)))));
+    g_cyc_mu[cls][mu < 0 ? 181 : mu]++;
+  }
+#endif
   if (nvc == 1 && vcs[0].count == 1) return runVelocityIterations1(e, vcs[0], velIters);
   if (nvc == 1 && vcs[0].count == 2) return runVelocityIterations2(e, vcs[0], velIters);
   const int budget = e.sweepBudget;
@@ -1225,6 +1246,9 @@ HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache&
     initConstraint(S, e, pid, slot, true, &vcs[nvc]);
     ++nvc;
   }
+#if defined(HK_CYCLE_STUDY) && !defined(__CUDA_ARCH__)
+  { extern void studySolve(const Env&, const int*, const VC*, int); studySolve(e, ic, vcs, nvc); }
+#endif
   if (nvc > 0) {
     for (int k = 0; k < nvc; ++k) warmStartConstraint(e, vcs[k]);
     int itc = runVelocityIterations(e, vcs, nvc, velIters);
@@ -1322,28 +1346,63 @@ HK_HD void bodyAdvance(const Scene& S, Body& b, int bi, float alpha) {  // b2Bod
   b.p = b.c - mul(b.q, s.lc);
 }
 
+// separation of an AABB (its corner deepest along -n) from the slanted inner face of a corner trapezoid (f = 2..5)
+HK_HD float slantedFaceGap(const Scene& S, int f, const AABB& b) {
+  const int k = (f & 1) ? 1 : 3;  // index of the slanted face in the hull order of polygons 2..5 (hk_scene.cuh)
+  const Poly& P = S.poly[f];
+  const float nx = P.nx[k], ny = P.ny[k];
+  const float px = P.vx[k] + S.spx[f], py = P.vy[k] + S.spy[f];
+  const float cx = nx > 0.0f ? b.lx : b.hx, cy = ny > 0.0f ? b.ly : b.hy;
+  return nx * (cx - px) + ny * (cy - py);
+}
+
 // Exact proof that b2TimeOfImpact cannot answer "touching" for static fixture fA vs body bi over this tick's sweep
 // (see the comment at its use in solveTOI).  Only valid before any TOI event, with the body's sweep start being the
 // pose Collide saw (the body went through this tick's island solve) and alpha0 == 0.
 HK_HD bool toiProvablySeparated(const Scene& S, const Env& e, int pid, int fA, int bi, float radiusB) {
   const Body& B = e.b[bi];
   V2 dc = B.c - B.c0;
-  float toward = -dot(e.sepNormal[pid], dc);
+  const V2 sn = e.sepNormal[pid];
+  // a zero normal marks a distance bound without a fixed direction: the whole displacement counts
+  float toward = (sn.x == 0.0f && sn.y == 0.0f) ? length(dc) : -dot(sn, dc);
   float disp = fmax2(toward, 0.0f) + (bi == B_PUCK ? 0.0f : 0.5f * fabs2(B.a - B.a0));
   float totalRadius = HK_POLYGON_RADIUS + radiusB;
   float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
   if (e.sepBound[pid] - disp > target + 0.25f * HK_LINEAR_SLOP + 0.002f) return true;
-  // second proof (same as the fast tier): the swept core AABB of the body stays clear of the static core AABB
   float da = fabs2(B.a - B.a0);
   if (bi != B_PUCK && da > 0.2f) return false;
   float sag = bi == B_PUCK ? 0.0f : 0.0625f * da * da;
+  // second proof (rackets): along a fixed face normal n of the static polygon every racket vertex moves on
+  // n.p(t) = linear + |r| cos(theta(t) + phi), which stays above the lower of its two end values minus the
+  // sagitta |r| da^2 / 8 (|r| <= 0.5 m) -- so the face separation during the sweep is at least
+  // min(start, end) - sag.  The start value is sepBound; the end value is evaluated here from the final pose.
+  if (bi != B_PUCK && !(sn.x == 0.0f && sn.y == 0.0f) && e.sepBound[pid] > 0.0f) {
+    const Poly& PA = S.poly[fA];
+    int k = -1;
+    for (int i = 0; i < PA.count; ++i)
+      if (PA.nx[i] == sn.x && PA.ny[i] == sn.y) k = i;
+    if (k >= 0) {
+      const Poly& PB = S.poly[F_R1 + bi];
+      const Xf xfB = bodyXf(B);
+      const float px = PA.vx[k] + S.spx[fA], py = PA.vy[k] + S.spy[fA];
+      float sEnd = HK_MAXFLOAT;
+      for (int i = 0; i < PB.count; ++i) {
+        V2 v = mul(xfB, polyV(PB, i));
+        sEnd = fmin2(sEnd, sn.x * (v.x - px) + sn.y * (v.y - py));
+      }
+      if (fmin2(e.sepBound[pid], sEnd) - sag - 0.001f > target + 0.25f * HK_LINEAR_SLOP + 0.002f) return true;
+    }
+  }
+  // third proof (same as the fast tier): the swept core AABB of the body stays clear of the static core AABB
   AABB st = S.sfat[fA];
   const float d = HK_AABB_EXTENSION + HK_POLYGON_RADIUS;
   st.lx += d; st.ly += d; st.hx -= d; st.hy -= d;
   AABB mv = e.swept[bi];
   mv.lx += radiusB; mv.ly += radiusB; mv.hx -= radiusB; mv.hy -= radiusB;
   float gx = fmax2(st.lx - mv.hx, mv.lx - st.hx), gy = fmax2(st.ly - mv.hy, mv.ly - st.hy);
-  return fmax2(gx, gy) > target + 0.25f * HK_LINEAR_SLOP + sag + 0.005f;
+  float gap = fmax2(gx, gy);
+  if (fA >= 2 && fA < 6) gap = fmax2(gap, slantedFaceGap(S, fA, mv));
+  return gap > target + 0.25f * HK_LINEAR_SLOP + sag + 0.005f;
 }
 
 // One first-pass TOI evaluation as a self-contained task (hk_lib.cu runs these block-wide, one task per thread,

@@ -259,8 +259,8 @@ def main():
                     "d2h_bytes_per_step": n * (72 + 4 + 1 + 16), "steps": args.e2e_steps,
                     "note": "player-1 actions from pinned host memory, obs/reward/done/info to pinned host memory, "
                             "host sync every tick; player 2 = in-kernel strong BasicOpponent"},
-            # kernels of this repo launched in the timed region: k_fast + the general tier(s) per tick
-            "gpu_launches": args.steps * (3 if (n >= 200000 and os.environ.get("HK_TIERS") != "2") or os.environ.get("HK_TIERS") == "3" else 2),
+            # kernels of this repo launched in the timed region: k_fast, k_touch and the general tier(s) per tick
+            "gpu_launches": args.steps * env.launches_per_step(),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 if n == 65536 else None,

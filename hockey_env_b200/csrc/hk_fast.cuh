@@ -23,7 +23,8 @@ namespace hk {
 
 #define HK_FAST_EPS 0.005f
 // bail reason -> work class of the general tier (hk_lib.cu sorts the slow queue by class so that the lanes of a
-// warp do the same kind of work): 0 keep/shoot tick, 1 racket against statics, 2 puck contacts / sensors, 3 other
+// warp do the same kind of work): 0 puck against a racket (keep/shoot ticks; these go through the touch tier first),
+// 1 racket against statics, 2 puck against statics / sensors, 3 other
 #if defined(HK_FAST_DEBUG) && !defined(__CUDA_ARCH__)
 extern long long g_fast_bail[16];
 #define HK_BAIL(k) do { g_fast_bail[k]++; e.bailKind = (k); return false; } while (0)
@@ -31,53 +32,17 @@ extern long long g_fast_bail[16];
 #define HK_BAIL(k) do { e.bailKind = (k); return false; } while (0)
 #endif
 HK_HD int bailClass(int kind) {
-  if (kind == 0) return 0;
+  if (kind == 0 || kind == 4) return 0;  // puck against a racket (keep/shoot ticks, plain hits): the touch tier
   if (kind == 6 || kind == 9 || kind == 8) return 1;
-  if (kind == 2 || kind == 3 || kind == 4 || kind == 10) return 2;
+  if (kind == 2 || kind == 3 || kind == 10) return 2;
   return 3;
 }
 
-HK_HD AABB staticCoreAABB(const Scene& S, int f) {  // fat box minus extension and skin (exact enough: eps >> rounding)
-  AABB r = S.sfat[f];
-  const float d = HK_AABB_EXTENSION + HK_POLYGON_RADIUS;
-  r.lx += d;
-  r.ly += d;
-  r.hx -= d;
-  r.hy -= d;
-  return r;
-}
-HK_HD float aabbGap(const AABB& a, const AABB& b) {
-  float gx = fmax2(a.lx - b.hx, b.lx - a.hx);
-  float gy = fmax2(a.ly - b.hy, b.ly - a.hy);
-  return fmax2(gx, gy);
-}
-// Largest separation of the racket's vertices from a face plane of static polygon f (statics have angle 0).  The
-// static polygons have four faces; b2FindMaxSeparation's hill climb (2.3.0) starts at the face best aligned with
-// the centroid direction, examines it and both neighbours and keeps the largest, and the start face cannot be the
-// one opposite a face that separates the shapes -- so whenever this value exceeds totalRadius the climb returns a
-// separation above totalRadius as well and b2CollidePolygons produces no manifold points.
-HK_HD float polyStaticFaceGap(const Scene& S, int f, const Poly& PB, const Xf& xfB, V2* normal) {
-  const Poly& PA = S.poly[f];
-  const float ox = S.spx[f], oy = S.spy[f];
-  float s0 = HK_MAXFLOAT, s1 = HK_MAXFLOAT, s2 = HK_MAXFLOAT, s3 = HK_MAXFLOAT;
-  for (int i = 0; i < PB.count; ++i) {
-    V2 v = mul(xfB, polyV(PB, i));
-    const float x = v.x - ox, y = v.y - oy;
-    s0 = fmin2(s0, PA.nx[0] * (x - PA.vx[0]) + PA.ny[0] * (y - PA.vy[0]));
-    s1 = fmin2(s1, PA.nx[1] * (x - PA.vx[1]) + PA.ny[1] * (y - PA.vy[1]));
-    s2 = fmin2(s2, PA.nx[2] * (x - PA.vx[2]) + PA.ny[2] * (y - PA.vy[2]));
-    s3 = fmin2(s3, PA.nx[3] * (x - PA.vx[3]) + PA.ny[3] * (y - PA.vy[3]));
-  }
-  int k = 0;
-  float best = s0;
-  if (s1 > best) { best = s1; k = 1; }
-  if (s2 > best) { best = s2; k = 2; }
-  if (s3 > best) { best = s3; k = 3; }
-  *normal = polyN(PA, k);
-  return best;
-}
-
-HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, Env& e) {
+// PUCK_RACKET = false: the contact-free fast tier.  PUCK_RACKET = true (touch tier): the puck x racket pairs are
+// updated exactly (b2Contact::Update with manifold, warm-start ids, BeginContact) and may touch; every other pair
+// must still be provably clear.
+template <bool PUCK_RACKET>
+HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   int i = 0;
   while (i < e.ncontacts) {
     int pid = clistGet(e.clist, i);
@@ -97,6 +62,11 @@ HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, Env& e) {
       e.exist &= ~bit;
       e.touch &= ~bit;
       setCount(e, pid, 0);
+      continue;
+    }
+    if (PUCK_RACKET && fB == F_PUCK && fA >= F_R1) {
+      updateContact(S, cfg, cache, e, pid);
+      ++i;
       continue;
     }
     e.enabled |= bit;
@@ -180,7 +150,10 @@ HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, flo
     e.moved &= ~8u;
     findNewContacts(S, e);
   }
-  if (!collideFast(S, cfg, e)) return false;  // bailKind set by collideFast
+  Cache none;
+  none.base = nullptr;
+  none.stride = 0;
+  if (!collideFast<false>(S, cfg, none, e)) return false;  // bailKind set by collideFast
   // ---- b2World::Solve with no constraints: every awake body is its own island ----
   Rot q0[3];
   for (int bi = 2; bi >= 0; --bi) {
@@ -231,6 +204,52 @@ HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, flo
     e.b[bi].f = mk(0.0f, 0.0f);
     e.b[bi].tq = 0.0f;
   }
+  return true;
+}
+
+// ---- touch tier: ticks whose only touching solid contacts are puck x racket (every keep/shoot tick: the puck is
+// teleported into the racket, hockey_env.py:618-620,668-680) and that provably have no continuous-collision event.
+// Collide is the fast one plus an exact update of the puck x racket pairs; the island solve is the general one
+// (hk_world.cuh: one contact, one manifold point -> the register-resident sweep loop, then the position iterations);
+// SolveTOI is replaced by the fast tier's proofs.  Returns false without side effects that matter otherwise.
+HK_HD_NOINLINE bool worldStepTouch(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h) {
+  e.enabled = 0xFFFFFFFFu;
+  e.nmf = 0;
+  e.toiEventSeen = false;
+  e.toiPreFlag = 0;
+  for (int k = 0; k < N_PAIRS; ++k) e.sepBound[k] = -HK_MAXFLOAT;
+  if (e.moved & 8u) {
+    e.moved &= ~8u;
+    findNewContacts(S, e);
+  }
+  if (!collideFast<true>(S, cfg, cache, e)) return false;
+  solveIslands(S, cfg, cache, e, h, 6 * 30, 2 * 30);
+  if (e.aborted) HK_BAIL(11);
+  uint32_t cand = e.exist & HK_PAIRS_TOI;
+  if (cand) {
+    for (int i = 0; i < e.ncontacts; ++i) {
+      int pid = clistGet(e.clist, i);
+      if (!((cand >> pid) & 1u)) continue;
+      int fA = S.pairFA[pid], fB = S.pairFB[pid];
+      int bi = fB - F_R1;
+      const Body& B = e.b[bi];
+      if (!B.awake) continue;
+      if (!B.island) HK_BAIL(7);
+      const float r = bi == B_PUCK ? S.puckRadius : HK_POLYGON_RADIUS;
+      if (!toiProvablySeparated(S, e, pid, fA, bi, r)) HK_BAIL(9 + (bi == B_PUCK ? 1 : 0));
+    }
+  }
+  e.b[0].island = e.b[1].island = e.b[2].island = false;
+  worldStepFinish(cache, e);
+  return true;
+}
+HK_HD bool envStepTouch(const Scene& S, const Config& cfg, const Cache& cache, Env& e, const float action[8]) {
+  envStepActions(S, cfg, e, action);
+  e.sweepBudget = 1 << 20;
+  e.allowToiEvents = true;
+  e.aborted = false;
+  if (!worldStepTouch(S, cfg, cache, e, (float)(1.0 / HK_FPS))) return false;
+  envStepAfterWorld(cfg, e);
   return true;
 }
 

@@ -112,6 +112,7 @@ struct KParams {
   uint32_t* qctl;    // queue counters, see Q_* below
   unsigned long long* phaseClk;  // [2 tiers][4 phases] block-cycles spent per phase (diagnostics, hk_debug_phase_cycles)
   float* actBuf;     // [n,8] actions handed from k_fast to the general tiers
+  uint32_t* trace;   // diagnostics (HK_LANE_TRACE=1): [n/32+8 warps][4] phase cycles, then [n][2] per-env work record
   int64_t n;
   int64_t env_id_offset;
   Config cfg;
@@ -210,6 +211,50 @@ __global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
   flushStats(P.stats, st);
 }
 
+// Touch tier: work class 0 of k_fast's queue (puck x racket contact ticks, i.e. every keep/shoot tick).  One contact,
+// one manifold point, no continuous-collision event possible -- the lanes of a warp all walk the same short path
+// (hk_fast.cuh worldStepTouch).  Envs whose proofs fail are appended to work class 3 for the general tier.
+__global__ void __launch_bounds__(kBlock) k_touch(KParams P, StepIO io) {
+  __shared__ Scene S;
+  stageScene(&S);
+  const int lane = threadIdx.x & 31;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned cnt = *((volatile uint32_t*)&P.qctl[0]);
+  const bool valid = j < (int64_t)cnt;
+  if (!__any_sync(0xffffffffu, valid)) return;
+  TickStats st;
+  tickStatsZero(st);
+  bool need = false;
+  int64_t i = 0;
+  if (valid) {
+    i = P.queue[j];
+    Env e;
+    loadEnv(P.core, P.n, i, e);
+    Cache cache;
+    cache.base = P.cache + i;
+    cache.stride = (size_t)P.n;
+    float a[8];
+    const float4* ab = reinterpret_cast<const float4*>(io.actBuf + 8 * i);
+    float4 lo = ab[0], hi = ab[1];
+    a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+    e.bailKind = 15;
+    if (envTickTouch(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st, a)) {
+      storeEnv(P.core, P.n, i, e);
+    } else {
+      tickStatsZero(st);
+      need = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, need);
+  if (m) {
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&P.qctl[Q_CLASSES - 1], (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (need) P.queue[(int64_t)(Q_CLASSES - 1) * P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+  }
+  flushStats(P.stats, st);
+}
+
 // Tier 1 and 2 of the cascade run the same general path (hk::envTick) over compacted queues:
 //   TIER == 1 (k_mid): budgeted -- a velocity solve must converge (fixed point / short cycle) within kMidSweeps
 //                      sweeps and no continuous-collision EVENT may occur; otherwise the env is appended to the
@@ -219,7 +264,7 @@ __global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
 //                      of each of them stalling 31 converged neighbours for up to 180 sweeps.
 constexpr int kMidSweeps = 24;
 template <int TIER>
-__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2) {
+__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass) {
   __shared__ Scene S;
   stageScene(&S);
   const int lane = threadIdx.x & 31;
@@ -234,7 +279,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     int64_t w0 = 0;
 #pragma unroll
     for (int c = 0; c < Q_CLASSES; ++c) {
-      const unsigned cnt = *((volatile uint32_t*)&P.qctl[c]);
+      const unsigned cnt = c < firstClass ? 0u : *((volatile uint32_t*)&P.qctl[c]);  // class 0 was k_touch's
       const int64_t nw = ((int64_t)cnt + lanes - 1) >> lanesLog2;
       if (!valid && gw >= w0 && gw < w0 + nw && lane < lanes) {
         const int64_t j = ((gw - w0) << lanesLog2) + lane;
@@ -284,9 +329,11 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     envStepActions(S, P.cfg, e, a);
     worldStepCollide(S, P.cfg, cache, e);
   }
+  const long long tw1 = clock64();
   __syncthreads();
   long long tc1 = clock64();
   if (valid) solveIslands(S, P.cfg, cache, e, dt, 6 * 30, 2 * 30);  // phase 2
+  const long long tw2 = clock64();
   __syncthreads();
   long long tc2 = clock64();
   // phase 3a-3c: first-pass TOI evaluations of the whole block as one task list, one task per thread
@@ -309,14 +356,26 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     }
     __syncthreads();
     const int total = sCount;
-    for (int t = threadIdx.x; t < total; t += blockDim.x) sAlpha[t] = toiTaskRun(S, sTasks[t]);
+    // tasks are dealt round-robin to the warps of the block (lane l of warp w takes task l * nwarps + w): the lanes
+    // of a warp diverge inside b2TimeOfImpact, so a warp's time grows with the number of tasks it holds
+    const int nwarps = blockDim.x >> 5;
+    for (int t = lane * nwarps + (threadIdx.x >> 5); t < total; t += blockDim.x) sAlpha[t] = toiTaskRun(S, sTasks[t]);
     __syncthreads();
     for (int k = 0; k < nMine; ++k) {
       e.toiPre[mine[k].pid] = sAlpha[base + k];
       e.toiPreFlag |= 1u << mine[k].pid;
     }
   }
+  const long long tw3a = clock64();
   if (wantToi) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3d: events (rare) on top of the pre-seeded results
+  const long long tw3 = clock64();
+  if (P.trace && TIER == 1 && lane == 0 && gw < P.n / 32 + 8) {
+    uint32_t* w = P.trace + 4 * (size_t)gw;
+    w[0] = (uint32_t)(tw1 - tc0);
+    w[1] = (uint32_t)(tw2 - tc1);
+    w[2] = (uint32_t)(tw3a - tc2);
+    w[3] = (uint32_t)(tw3 - tw3a);
+  }
   __syncthreads();
   long long tc3 = clock64();
   {  // diagnostics: block-wide max of per-lane TOI evaluation / event cycles
@@ -332,6 +391,12 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
       atomicAdd(&P.phaseClk[4], sMaxEval);
       atomicAdd(&P.phaseClk[5], sMaxEvent);
     }
+  }
+  if (P.trace && TIER == 1 && valid) {
+    uint32_t* rec = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)i;
+    rec[0] = (e.nVelIters & 0xFFFu) | ((e.nToiEvents & 0xFu) << 12) | ((uint32_t)(e.bailKind & 0xF) << 16) | ((e.dbgShape & 0xFFu) << 20) |
+             (e.aborted ? 0x80000000u : 0u);
+    rec[1] = (uint32_t)gw;
   }
   if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
     if (!e.aborted) {
@@ -480,6 +545,7 @@ struct hk_env {
   uint32_t* qctl;
   unsigned long long* phaseClk;
   float* actBuf;
+  uint32_t* trace;
   int tiers;  // HK_TIERS=2: fast + unlimited general tier; 3 (default): fast + budgeted + unlimited
   bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
@@ -491,6 +557,7 @@ struct hk_env {
     P.qctl = qctl;
     P.phaseClk = phaseClk;
     P.actBuf = actBuf;
+    P.trace = trace;
     P.n = n;
     P.env_id_offset = env_id_offset;
     P.cfg = cfg;
@@ -514,6 +581,17 @@ struct hk_env {
     return (int)b;
   }
   int lanes1, lanes2;  // log2 envs per warp in tier 1 / tier 2 (HK_LANES1 / HK_LANES2 override)
+  bool touch;          // HK_TOUCH=0 disables the touch tier (A/B measurements)
+  int launches;        // kernels per tick of the cascade
+  // one tick: k_fast over all envs, k_touch over work class 0, the general tier(s) over the rest
+  void launchCascade(const StepIO& io, cudaStream_t stream) const {
+    if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (4 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
+    k_fast<<<grid(), kBlock, 0, stream>>>(params(), io);
+    if (touch) k_touch<<<grid(), kBlock, 0, stream>>>(params(), io);
+    const int b1 = blockFor(touch ? 0.15 : 0.75), b2 = blockFor(0.06);
+    k_general<1><<<gridSlow(lanes1, b1), b1, 0, stream>>>(params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0);
+    if (tiers == 3) k_general<2><<<gridSlow(lanes2, b2), b2, 0, stream>>>(params(), io, 1, lanes2, 0);
+  }
 };
 
 static bool validPolicy(int p) { return p >= HK_POLICY_EXTERNAL && p <= HK_POLICY_ZERO; }
@@ -550,6 +628,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   h->qctl = nullptr;
   h->phaseClk = nullptr;
   h->actBuf = nullptr;
+  h->trace = nullptr;
   {
     const char* m = getenv("HK_MONO");
     h->mono = m && m[0] == '1';
@@ -564,6 +643,12 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     if (const char* l2 = getenv("HK_LANES2")) h->lanes2 = atoi(l2);
     if (h->lanes1 < 0 || h->lanes1 > 5) h->lanes1 = 5;
     if (h->lanes2 < 0 || h->lanes2 > 5) h->lanes2 = 5;
+    // measured (profiles/README.md): below ~200k envs a tick is bound by its slowest env, and a separate kernel for
+    // the puck-racket ticks only adds a launch in front of that critical path; above, it pays (homogeneous lanes)
+    const char* tt = getenv("HK_TOUCH");
+    h->touch = n_envs >= 200000;
+    if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
+    h->launches = h->mono ? 1 : 2 + (h->touch ? 1 : 0) + (h->tiers == 3 ? 1 : 0);
   }
   Scene S;
   std::memset(&S, 0, sizeof(S));
@@ -578,6 +663,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->actBuf, sizeof(float) * 8 * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->phaseClk, sizeof(unsigned long long) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 8);
+  if (err == cudaSuccess && getenv("HK_LANE_TRACE")) err = cudaMalloc(&h->trace, sizeof(uint32_t) * (4 * ((size_t)n_envs / 32 + 8) + 2 * (size_t)n_envs));
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
   if (err == cudaSuccess) {
@@ -594,6 +680,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     cudaFree(h->qctl);
     cudaFree(h->phaseClk);
     cudaFree(h->actBuf);
+    cudaFree(h->trace);
     delete h;
     return fail(HK_E_CUDA, msg);
   }
@@ -611,6 +698,7 @@ int hk_destroy(hk_env* h) {
   cudaFree(h->qctl);
   cudaFree(h->phaseClk);
   cudaFree(h->actBuf);
+  cudaFree(h->trace);
   delete h;
   return HK_OK;
 }
@@ -657,11 +745,7 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
     k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
   } else {
     io.actBuf = h->actBuf;
-    k_fast<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
-    const int b1 = h->blockFor(0.5), b2 = h->blockFor(0.1);
-    k_general<1><<<h->gridSlow(h->lanes1, b1), b1, 0, (cudaStream_t)stream>>>(h->params(), io, h->tiers == 2 ? 1 : 0, h->lanes1);
-    if (h->tiers == 3)
-      k_general<2><<<h->gridSlow(h->lanes2, b2), b2, 0, (cudaStream_t)stream>>>(h->params(), io, 1, h->lanes2);
+    h->launchCascade(io, (cudaStream_t)stream);
   }
   HK_CUDA(cudaGetLastError());
   return HK_OK;
@@ -684,13 +768,9 @@ int hk_rollout(hk_env* h, int k_steps, int p1_policy, int p2_policy, float* obs_
     k_rollout<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io, k_steps);
   } else {        // K ticks of the kernel cascade back to back; only the last tick writes its observation
     io.actBuf = h->actBuf;
-    const int b1 = h->blockFor(0.5), b2 = h->blockFor(0.1);
     for (int s = 0; s < k_steps; ++s) {
       io.write = (s == k_steps - 1 && obs_dev) ? 1 : 0;
-      k_fast<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
-      k_general<1><<<h->gridSlow(h->lanes1, b1), b1, 0, (cudaStream_t)stream>>>(h->params(), io, h->tiers == 2 ? 1 : 0, h->lanes1);
-      if (h->tiers == 3)
-        k_general<2><<<h->gridSlow(h->lanes2, b2), b2, 0, (cudaStream_t)stream>>>(h->params(), io, 1, h->lanes2);
+      h->launchCascade(io, (cudaStream_t)stream);
     }
   }
   HK_CUDA(cudaGetLastError());
@@ -767,6 +847,17 @@ int hk_debug_phase_cycles(hk_env* h, double* out_host8) {
   for (int k = 0; k < 8; ++k) out_host8[k] = (double)v[k];
   return HK_OK;
 }
+
+int hk_debug_lane_trace(hk_env* h, uint32_t* out_host, int64_t n_words) {
+  if (!h || !out_host) return fail(HK_E_INVALID, "hk_debug_lane_trace: NULL argument");
+  if (!h->trace) return fail(HK_E_INVALID, "hk_debug_lane_trace: create the env with HK_LANE_TRACE=1");
+  const int64_t have = 4 * (h->n / 32 + 8) + 2 * h->n;
+  DeviceGuard guard(h->device);
+  HK_CUDA(cudaMemcpy(out_host, h->trace, sizeof(uint32_t) * (size_t)(n_words < have ? n_words : have), cudaMemcpyDeviceToHost));
+  return HK_OK;
+}
+
+int hk_launches_per_step(const hk_env* h) { return h ? h->launches : 0; }
 
 int hk_stats_device_ptr(hk_env* h, double** out_dev) {
   if (!h || !out_dev) return fail(HK_E_INVALID, "hk_stats_device_ptr: NULL argument");

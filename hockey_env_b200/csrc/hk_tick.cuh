@@ -137,6 +137,24 @@ HK_HD bool envTickFast(const Scene& S, const Config& cfg, Env& e, uint64_t env_i
   return true;
 }
 
+// touch-tier tick (hk_fast.cuh worldStepTouch).  `pre` = this tick's clipped actions if the fast tier already ran the
+// controllers (then only their phase side effect is applied), else null.  Returns false -- nothing committed, e
+// unusable -- if the env needs the general path.
+HK_HD bool envTickTouch(const Scene& S, const Config& cfg, const Cache& cache, Env& e, uint64_t env_id, size_t i,
+                        const StepIO& io, bool write, TickStats& st, const float* pre) {
+  float a[8];
+  if (pre) {
+    for (int k = 0; k < 8; ++k) a[k] = pre[k];
+    policyAdvancePhases(cfg, e, env_id, io.pol1, io.pol2);
+  } else {
+    policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+  }
+  const int had1 = e.has1, had2 = e.has2;
+  if (!envStepTouch(S, cfg, cache, e, a)) return false;
+  tickFinish(S, cfg, e, env_id, i, io, write, st, had1, had2);
+  return true;
+}
+
 // HockeyEnv.__init__ for one env (hockey_env.py:91-155): phases of the built-in controllers
 // (BasicOpponent.__init__, :785), then reset(one_starting=True)
 HK_HD void envCreate(const Scene& S, const Config& cfg, Env& e, uint64_t env_id) {

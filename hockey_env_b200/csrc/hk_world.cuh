@@ -99,6 +99,7 @@ struct Env {
   // counters (statistics)
   uint32_t nVelIters, nToiEvents, nOverflow;
   long long dbgEvalClk, dbgEventClk;  // diagnostics: cycles this lane spent in TOI evaluation / event handling
+  uint32_t dbgShape;                  // diagnostics: contacts | manifold points << 4 of this tick's island solve
   // budgets of this tier (hk_lib.cu cascade); exceeding one sets `aborted` and the tick is redone, from the
   // stored state, by the next tier.  Nothing is committed before the end of a tick, so aborting is free.
   int sweepBudget;   // max velocity sweeps a solve may need to converge (>= 180: unlimited)
@@ -315,12 +316,65 @@ HK_HD int findSlot(const Env& e, int pid) {
   return -1;
 }
 
+HK_HD AABB staticCoreAABB(const Scene& S, int f) {  // fat box minus extension and skin (exact enough: eps >> rounding)
+  AABB r = S.sfat[f];
+  const float d = HK_AABB_EXTENSION + HK_POLYGON_RADIUS;
+  r.lx += d;
+  r.ly += d;
+  r.hx -= d;
+  r.hy -= d;
+  return r;
+}
+HK_HD float aabbGap(const AABB& a, const AABB& b) {
+  float gx = fmax2(a.lx - b.hx, b.lx - a.hx);
+  float gy = fmax2(a.ly - b.hy, b.ly - a.hy);
+  return fmax2(gx, gy);
+}
+// Largest separation of the racket's vertices from a face plane of static polygon f (statics have angle 0).  The
+// static polygons have four faces; b2FindMaxSeparation's hill climb (2.3.0) starts at the face best aligned with
+// the centroid direction, examines it and both neighbours and keeps the largest, and the start face cannot be the
+// one opposite a face that separates the shapes -- so whenever this value exceeds totalRadius the climb returns a
+// separation above totalRadius as well and b2CollidePolygons produces no manifold points.
+HK_HD float polyStaticFaceGap(const Scene& S, int f, const Poly& PB, const Xf& xfB, V2* normal) {
+  const Poly& PA = S.poly[f];
+  const float ox = S.spx[f], oy = S.spy[f];
+  float s0 = HK_MAXFLOAT, s1 = HK_MAXFLOAT, s2 = HK_MAXFLOAT, s3 = HK_MAXFLOAT;
+  for (int i = 0; i < PB.count; ++i) {
+    V2 v = mul(xfB, polyV(PB, i));
+    const float x = v.x - ox, y = v.y - oy;
+    s0 = fmin2(s0, PA.nx[0] * (x - PA.vx[0]) + PA.ny[0] * (y - PA.vy[0]));
+    s1 = fmin2(s1, PA.nx[1] * (x - PA.vx[1]) + PA.ny[1] * (y - PA.vy[1]));
+    s2 = fmin2(s2, PA.nx[2] * (x - PA.vx[2]) + PA.ny[2] * (y - PA.vy[2]));
+    s3 = fmin2(s3, PA.nx[3] * (x - PA.vx[3]) + PA.ny[3] * (y - PA.vy[3]));
+  }
+  int k = 0;
+  float best = s0;
+  if (s1 > best) { best = s1; k = 1; }
+  if (s2 > best) { best = s2; k = 2; }
+  if (s3 > best) { best = s3; k = 3; }
+  *normal = polyN(PA, k);
+  return best;
+}
+
 HK_HD_NOINLINE void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
   int fA = S.pairFA[pid], fB = S.pairFB[pid];
   Xf xfA = fixtureXf(S, e, fA);
   if (fB == F_PUCK) {
     collidePolygonCircle(m, S.poly[fA], xfA, e.b[B_PUCK].p, S.puckRadius);
   } else {
+    if (fA < N_STATIC_FIX) {
+      // racket against a static polygon: most candidate pairs are nowhere near touching.  A face of the static
+      // polygon that clears every racket vertex by more than totalRadius proves the manifold empty (see
+      // polyStaticFaceGap) at a fraction of b2CollidePolygons' two max-separation searches.
+      V2 nrm;
+      const float gap = polyStaticFaceGap(S, fA, S.poly[fB], bodyXf(e.b[fB - F_R1]), &nrm);
+      if (gap > 2.0f * HK_POLYGON_RADIUS + 0.0005f) {
+        m->count = 0;
+        m->sepBound = gap - 0.001f;
+        m->sepNormal = nrm;
+        return;
+      }
+    }
     collidePolygons(m, S.poly[fA], xfA, S.poly[fB], bodyXf(e.b[fB - F_R1]));
   }
 }
@@ -335,7 +389,14 @@ HK_HD_NOINLINE void updateContact(const Scene& S, const Config& cfg, const Cache
   bool touching;
   if ((HK_PAIRS_SENSOR >> pid) & 1u) {
     int fA = S.pairFA[pid];
-    touching = testOverlapPolyPuck(S.poly[fA], staticXf(S, fA), e.b[B_PUCK].p, S.puckRadius);
+    // the GJK overlap test only when the puck centre is within reach of the goal box (margin >> float rounding)
+    AABB core = staticCoreAABB(S, fA);
+    V2 c = e.b[B_PUCK].p;
+    AABB pb;
+    pb.lx = pb.hx = c.x;
+    pb.ly = pb.hy = c.y;
+    if (aabbGap(core, pb) > S.puckRadius + HK_POLYGON_RADIUS + 0.005f) touching = false;
+    else touching = testOverlapPolyPuck(S.poly[fA], staticXf(S, fA), e.b[B_PUCK].p, S.puckRadius);
   } else {
     int slot = findSlot(e, pid);
     Manifold tmp;
@@ -725,44 +786,6 @@ HK_HD_NOINLINE bool solveVelocityConstraint(Env& e, VC& vc) {
 //    an impulse and of a velocity flip back and forth) -- the state after all N sweeps is s_k or s_(k-1)
 //    depending on the parity of N - k.
 // Either way the result is numerically identical to running all N sweeps, which is what the oracle does.
-struct SolveSnap {
-  float v[9];
-  float imp[MAX_MANIFOLDS * 4];
-};
-HK_HD_NOINLINE void snapSave(const Env& e, const VC* vcs, int nvc, SolveSnap& s) {
-  for (int b = 0; b < 3; ++b) {
-    s.v[3 * b] = e.b[b].v.x;
-    s.v[3 * b + 1] = e.b[b].v.y;
-    s.v[3 * b + 2] = e.b[b].w;
-  }
-  for (int k = 0; k < nvc; ++k) {
-    s.imp[4 * k] = vcs[k].pt[0].ni;
-    s.imp[4 * k + 1] = vcs[k].pt[0].ti;
-    s.imp[4 * k + 2] = vcs[k].count > 1 ? vcs[k].pt[1].ni : 0.0f;
-    s.imp[4 * k + 3] = vcs[k].count > 1 ? vcs[k].pt[1].ti : 0.0f;
-  }
-}
-HK_HD_NOINLINE bool snapEqual(const SolveSnap& a, const SolveSnap& b, int nvc) {
-  for (int i = 0; i < 4 * nvc; ++i)  // impulses first: they are what still moves when the velocities have settled
-    if (!(a.imp[i] == b.imp[i])) return false;
-  for (int i = 0; i < 9; ++i)
-    if (!(a.v[i] == b.v[i])) return false;
-  return true;
-}
-HK_HD_NOINLINE void snapRestore(Env& e, VC* vcs, int nvc, const SolveSnap& s) {
-  for (int b = 0; b < 3; ++b) {
-    e.b[b].v = mk(s.v[3 * b], s.v[3 * b + 1]);
-    e.b[b].w = s.v[3 * b + 2];
-  }
-  for (int k = 0; k < nvc; ++k) {
-    vcs[k].pt[0].ni = s.imp[4 * k];
-    vcs[k].pt[0].ti = s.imp[4 * k + 1];
-    if (vcs[k].count > 1) {
-      vcs[k].pt[1].ni = s.imp[4 * k + 2];
-      vcs[k].pt[1].ti = s.imp[4 * k + 3];
-    }
-  }
-}
 // Specialised sweep loop for the dominant case -- one contact with one manifold point (95 % of solves): every
 // quantity lives in registers, same expression order as solveVelocityConstraint().
 HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
@@ -975,73 +998,334 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
   return result;
 }
 
-// general loop: any number of contacts; fixed point and period-2 detection
-// returns the number of sweeps executed, or -1 if the tier's sweep budget ran out before the state repeated
-HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
-#if defined(HK_CYCLE_STUDY) && !defined(__CUDA_ARCH__)
-  {
-    Env e2 = e;
-    VC v2[MAX_MANIFOLDS];
-    for (int k = 0; k < nvc; ++k) v2[k] = vcs[k];
-    static SolveSnap hist[181];
-    for (int it = 0; it < velIters; ++it) {
-      for (int k = 0; k < nvc; ++k) solveVelocityConstraint(e2, v2[k]);
-      memset(&hist[it], 0, sizeof(SolveSnap));
-      snapSave(e2, v2, nvc, hist[it]);
-    }
-    int lam = 0;
-    for (int p = 1; p <= 90; ++p) if (snapEqual(hist[velIters - 1], hist[velIters - 1 - p], nvc)) { lam = p; break; }
-    int mu = -1;
-    if (lam) for (int i = 0; i + lam < velIters; ++i) if (snapEqual(hist[i], hist[i + lam], nvc)) { mu = i; break; }
-    extern long long g_cyc_lam[64], g_cyc_mu[8][182];
-    g_cyc_lam[lam < 63 ? lam : 63]++;
-    int cls = lam == 0 ? 0 : (lam == 1 ? 1 : (lam == 2 ? 2 : (lam <= 4 ? 3 : (lam <= 8 ? 4 : (lam <= 16 ? 5 : 6)))));
-    g_cyc_mu[cls][mu < 0 ? 181 : mu]++;
+// ---- general loop: any number of contacts ------------------------------------------------------------------
+// The constraint being swept lives in registers (VCR); the next one is loaded while the current one is computed
+// (its loads do not depend on the arithmetic chain, so their latency hides behind it) and only the accumulated
+// impulses go back to memory.  The three bodies' velocities and their values after the previous two sweeps are
+// registers as well; the impulse history needed for the period-2 test is a write-only rotating snapshot that is
+// read back only when all nine velocity components already repeat.
+struct VCR {
+  V2 normal;
+  float friction, mA, iA, mB, iB;
+  int bA, bB, count;
+  V2 rA0, rB0, rA1, rB1;
+  float nm0, tm0, bias0, ni0, ti0, nm1, tm1, bias1, ni1, ti1;
+  float k11, k12, k22, n11, n12, n21, n22;
+};
+HK_HD void vcrLoad(VCR& r, const VC& m) {
+  r.normal = m.normal;
+  r.friction = m.friction;
+  r.mA = m.mA; r.iA = m.iA; r.mB = m.mB; r.iB = m.iB;
+  r.bA = m.bA; r.bB = m.bB; r.count = m.count;
+  r.rA0 = m.pt[0].rA; r.rB0 = m.pt[0].rB;
+  r.nm0 = m.pt[0].normalMass; r.tm0 = m.pt[0].tangentMass; r.bias0 = m.pt[0].bias;
+  r.ni0 = m.pt[0].ni; r.ti0 = m.pt[0].ti;
+  if (m.count == 2) {
+    r.rA1 = m.pt[1].rA; r.rB1 = m.pt[1].rB;
+    r.nm1 = m.pt[1].normalMass; r.tm1 = m.pt[1].tangentMass; r.bias1 = m.pt[1].bias;
+    r.ni1 = m.pt[1].ni; r.ti1 = m.pt[1].ti;
+    r.k11 = m.k11; r.k12 = m.k12; r.k22 = m.k22;
+    r.n11 = m.n11; r.n12 = m.n12; r.n21 = m.n21; r.n22 = m.n22;
+  } else {
+    r.rA1 = r.rB1 = mk(0.0f, 0.0f);
+    r.nm1 = r.tm1 = r.bias1 = r.ni1 = r.ti1 = 0.0f;
+    r.k11 = r.k12 = r.k22 = r.n11 = r.n12 = r.n21 = r.n22 = 0.0f;
   }
-#endif
-  if (nvc == 1 && vcs[0].count == 1) return runVelocityIterations1(e, vcs[0], velIters);
-  if (nvc == 1 && vcs[0].count == 2) return runVelocityIterations2(e, vcs[0], velIters);
-  const int budget = e.sweepBudget;
-  int sweeps = 0;
-  SolveSnap snaps[3];  // rotating: [it % 3] = state after sweep it (so (it-1) % 3 and (it-2) % 3 are the two before)
-  const int kFirstSnap = 2;
-  // the three bodies' velocities stay in registers for the whole loop (selected by index, no local-memory round trips)
-  Vel v0 = loadVel(e, 0), v1 = loadVel(e, 1), v2 = loadVel(e, 2);
+}
+// one Gauss-Seidel pass over one contact held in registers: same expression order as solveVelocityConstraintCore()
+template <int COUNT>  // COUNT = 1 / 2: manifold points known at compile time; 0: read c.count
+HK_HD bool vcrSweep(VCR& c, Vel& A, Vel& B) {
+  bool changed = false;
+  const float mA = c.mA, iA = c.iA, mB = c.mB, iB = c.iB;
+  V2 vA = A.v, vB = B.v;
+  float wA = A.w, wB = B.w;
+  const V2 normal = c.normal;
+  const V2 tangent = cross(normal, 1.0f);
+  {  // tangent, point 0
+    V2 dv = vB + cross(wB, c.rB0) - vA - cross(wA, c.rA0);
+    float vt = dot(dv, tangent) - 0.0f;
+    float lambda = c.tm0 * (-vt);
+    float maxFriction = c.friction * c.ni0;
+    float newImpulse = fclamp(c.ti0 + lambda, -maxFriction, maxFriction);
+    lambda = newImpulse - c.ti0;
+    c.ti0 = newImpulse;
+    changed = changed || (lambda != 0.0f);
+    V2 P = lambda * tangent;
+    vA -= mA * P;
+    wA -= iA * cross(c.rA0, P);
+    vB += mB * P;
+    wB += iB * cross(c.rB0, P);
+  }
+  if (COUNT == 1 || (COUNT == 0 && c.count == 1)) {
+    V2 dv = vB + cross(wB, c.rB0) - vA - cross(wA, c.rA0);
+    float vn = dot(dv, normal);
+    float lambda = -c.nm0 * (vn - c.bias0);
+    float newImpulse = fmax2(c.ni0 + lambda, 0.0f);
+    lambda = newImpulse - c.ni0;
+    c.ni0 = newImpulse;
+    changed = changed || (lambda != 0.0f);
+    V2 P = lambda * normal;
+    vA -= mA * P;
+    wA -= iA * cross(c.rA0, P);
+    vB += mB * P;
+    wB += iB * cross(c.rB0, P);
+  } else {
+    {  // tangent, point 1
+      V2 dv = vB + cross(wB, c.rB1) - vA - cross(wA, c.rA1);
+      float vt = dot(dv, tangent) - 0.0f;
+      float lambda = c.tm1 * (-vt);
+      float maxFriction = c.friction * c.ni1;
+      float newImpulse = fclamp(c.ti1 + lambda, -maxFriction, maxFriction);
+      lambda = newImpulse - c.ti1;
+      c.ti1 = newImpulse;
+      changed = changed || (lambda != 0.0f);
+      V2 P = lambda * tangent;
+      vA -= mA * P;
+      wA -= iA * cross(c.rA1, P);
+      vB += mB * P;
+      wB += iB * cross(c.rB1, P);
+    }
+    // block solver
+    V2 a = mk(c.ni0, c.ni1);
+    V2 dv1 = vB + cross(wB, c.rB0) - vA - cross(wA, c.rA0);
+    V2 dv2 = vB + cross(wB, c.rB1) - vA - cross(wA, c.rA1);
+    float vn1 = dot(dv1, normal);
+    float vn2 = dot(dv2, normal);
+    V2 b;
+    b.x = vn1 - c.bias0;
+    b.y = vn2 - c.bias1;
+    b -= mk(c.k11 * a.x + c.k12 * a.y, c.k12 * a.x + c.k22 * a.y);
+    V2 x;
+    bool found = false;
+    x = -mk(c.n11 * b.x + c.n12 * b.y, c.n21 * b.x + c.n22 * b.y);
+    if (x.x >= 0.0f && x.y >= 0.0f) found = true;
+    if (!found) {
+      x.x = -c.nm0 * b.x;
+      x.y = 0.0f;
+      vn2 = c.k12 * x.x + b.y;
+      if (x.x >= 0.0f && vn2 >= 0.0f) found = true;
+    }
+    if (!found) {
+      x.x = 0.0f;
+      x.y = -c.nm1 * b.y;
+      vn1 = c.k12 * x.y + b.x;
+      if (x.y >= 0.0f && vn1 >= 0.0f) found = true;
+    }
+    if (!found) {
+      x.x = 0.0f;
+      x.y = 0.0f;
+      vn1 = b.x;
+      vn2 = b.y;
+      if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
+    }
+    if (found) {
+      V2 d = x - a;
+      V2 P1 = d.x * normal, P2 = d.y * normal;
+      vA -= mA * (P1 + P2);
+      wA -= iA * (cross(c.rA0, P1) + cross(c.rA1, P2));
+      vB += mB * (P1 + P2);
+      wB += iB * (cross(c.rB0, P1) + cross(c.rB1, P2));
+      c.ni0 = x.x;
+      c.ni1 = x.y;
+      changed = changed || (d.x != 0.0f) || (d.y != 0.0f);
+    }
+  }
+  A.v = vA;
+  A.w = wA;
+  B.v = vB;
+  B.w = wB;
+  return changed;
+}
+HK_HD bool velEq(const Vel& a, const Vel& b) { return a.v.x == b.v.x && a.v.y == b.v.y && a.w == b.w; }
+
+// sweep constraint k (held in c) against the register-resident body velocities, write its impulses back
+HK_HD bool vcrStep(VCR& c, int k, Vel& v0, Vel& v1, Vel& v2, VC* vcs, float* h) {
   Vel zero;
   zero.v = mk(0.0f, 0.0f);
   zero.w = 0.0f;
-  int it = 0;
+  const int bA = c.bA, bB = c.bB;
+  Vel A = bA == 0 ? v0 : (bA == 1 ? v1 : (bA == 2 ? v2 : zero));
+  Vel B = bB == 0 ? v0 : (bB == 1 ? v1 : (bB == 2 ? v2 : zero));
+  const bool changed = vcrSweep<0>(c, A, B);
+  if (bA == 0) v0 = A; else if (bA == 1) v1 = A; else if (bA == 2) v2 = A;
+  if (bB == 0) v0 = B; else if (bB == 1) v1 = B; else if (bB == 2) v2 = B;
+  vcs[k].pt[0].ni = c.ni0;
+  vcs[k].pt[0].ti = c.ti0;
+  h[4 * k] = c.ni0;
+  h[4 * k + 1] = c.ti0;
+  if (c.count == 2) {
+    vcs[k].pt[1].ni = c.ni1;
+    vcs[k].pt[1].ti = c.ti1;
+  }
+  h[4 * k + 2] = c.ni1;
+  h[4 * k + 3] = c.ti1;
+  return changed;
+}
+
+// ---- fixed shapes: two contacts (point counts C0, C1), everything in registers for the whole loop ------------
+// The tick time of a small batch is the time of its slowest env, and the slowest envs are the solves that never
+// settle (racket pressed on a bar while it holds the puck: two or three contacts, all 180 sweeps).  For them the
+// loop below has no memory traffic at all: both constraints, the three body velocities and the two previous states
+// needed for the period-2 test are registers; the point counts are template parameters.
+struct VelTriple {
+  Vel b0, b1, b2;
+};
+template <int COUNT>
+HK_HD bool vcrStepR(VCR& c, VelTriple& v) {
+  Vel zero;
+  zero.v = mk(0.0f, 0.0f);
+  zero.w = 0.0f;
+  const int bA = c.bA, bB = c.bB;
+  Vel A = bA == 0 ? v.b0 : (bA == 1 ? v.b1 : (bA == 2 ? v.b2 : zero));
+  Vel B = bB == 0 ? v.b0 : (bB == 1 ? v.b1 : (bB == 2 ? v.b2 : zero));
+  const bool changed = vcrSweep<COUNT>(c, A, B);
+  if (bA == 0) v.b0 = A; else if (bA == 1) v.b1 = A; else if (bA == 2) v.b2 = A;
+  if (bB == 0) v.b0 = B; else if (bB == 1) v.b1 = B; else if (bB == 2) v.b2 = B;
+  return changed;
+}
+struct Imp4 {
+  float ni0, ti0, ni1, ti1;
+};
+HK_HD Imp4 impOf(const VCR& c) {
+  Imp4 r;
+  r.ni0 = c.ni0; r.ti0 = c.ti0; r.ni1 = c.ni1; r.ti1 = c.ti1;
+  return r;
+}
+HK_HD void impTo(VCR& c, const Imp4& r) {
+  c.ni0 = r.ni0; c.ti0 = r.ti0; c.ni1 = r.ni1; c.ti1 = r.ti1;
+}
+template <int COUNT>
+HK_HD bool impEq(const VCR& c, const Imp4& r) {
+  return c.ni0 == r.ni0 && c.ti0 == r.ti0 && (COUNT == 1 || (c.ni1 == r.ni1 && c.ti1 == r.ti1));
+}
+HK_HD bool velTripleEq(const VelTriple& a, const VelTriple& b) { return velEq(a.b0, b.b0) && velEq(a.b1, b.b1) && velEq(a.b2, b.b2); }
+HK_HD void vcrStoreImpulses(const VCR& c, VC& m) {
+  m.pt[0].ni = c.ni0;
+  m.pt[0].ti = c.ti0;
+  if (m.count == 2) {
+    m.pt[1].ni = c.ni1;
+    m.pt[1].ti = c.ti1;
+  }
+}
+template <int C0, int C1, int C2>  // C2 == 0: two contacts
+HK_HD_NOINLINE int runVelocityIterationsFixed(Env& e, VC* vcs, int velIters) {
+  const int budget = e.sweepBudget;
+  int sweeps = 0;
+  VCR a, b, c;
+  vcrLoad(a, vcs[0]);
+  vcrLoad(b, vcs[1]);
+  if (C2 != 0) vcrLoad(c, vcs[2]);
+  VelTriple v, p, q;  // now, after the previous sweep, after the one before
+  v.b0 = loadVel(e, 0);
+  v.b1 = loadVel(e, 1);
+  v.b2 = loadVel(e, 2);
+  p = v;
+  q = v;
+  Imp4 pa = impOf(a), pb = impOf(b), pc = impOf(C2 != 0 ? c : a), qa = pa, qb = pb, qc = pc;
   int result = 0;
-  for (; it < velIters; ++it) {
+  for (int it = 0; it < velIters; ++it) {
+    bool changed = vcrStepR<C0>(a, v);
+    changed = vcrStepR<C1>(b, v) || changed;
+    if (C2 != 0) changed = vcrStepR<C2 == 0 ? 1 : C2>(c, v) || changed;
+    ++sweeps;
+    result = it + 1;
+    if (!changed) break;
+    if (it >= 2 && velTripleEq(v, q) && impEq<C0>(a, qa) && impEq<C1>(b, qb) && (C2 == 0 || impEq<C2 == 0 ? 1 : C2>(c, qc))) {
+      const int remaining = velIters - 1 - it;  // period-2 cycle: state after sweep it == state after sweep it - 2
+      if (remaining & 1) {
+        v = p;
+        impTo(a, pa);
+        impTo(b, pb);
+        if (C2 != 0) impTo(c, pc);
+      }
+      break;
+    }
+    q = p;
+    qa = pa; qb = pb;
+    p = v;
+    pa = impOf(a); pb = impOf(b);
+    if (C2 != 0) {
+      qc = pc;
+      pc = impOf(c);
+    }
+    if (it + 1 >= budget && it + 1 < velIters) {
+      result = -1;
+      break;
+    }
+  }
+  vcrStoreImpulses(a, vcs[0]);
+  vcrStoreImpulses(b, vcs[1]);
+  if (C2 != 0) vcrStoreImpulses(c, vcs[2]);
+  storeVel(e, 0, v.b0);
+  storeVel(e, 1, v.b1);
+  storeVel(e, 2, v.b2);
+  e.nVelIters += (uint32_t)sweeps;
+  return result;
+}
+
+// returns the number of sweeps executed, or -1 if the tier's sweep budget ran out before the state repeated
+HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
+  if (nvc == 1 && vcs[0].count == 1) return runVelocityIterations1(e, vcs[0], velIters);
+  if (nvc == 1 && vcs[0].count == 2) return runVelocityIterations2(e, vcs[0], velIters);
+  if (nvc == 2) {
+    const int c0 = vcs[0].count, c1 = vcs[1].count;
+    if (c0 == 1 && c1 == 1) return runVelocityIterationsFixed<1, 1, 0>(e, vcs, velIters);
+    if (c0 == 1 && c1 == 2) return runVelocityIterationsFixed<1, 2, 0>(e, vcs, velIters);
+    if (c0 == 2 && c1 == 1) return runVelocityIterationsFixed<2, 1, 0>(e, vcs, velIters);
+    return runVelocityIterationsFixed<2, 2, 0>(e, vcs, velIters);
+  }
+  if (nvc == 3 && vcs[0].count == 1 && vcs[1].count == 1 && vcs[2].count == 1)
+    return runVelocityIterationsFixed<1, 1, 1>(e, vcs, velIters);
+  const int budget = e.sweepBudget;
+  int sweeps = 0;
+  float hist[3][MAX_MANIFOLDS * 4];  // [it % 3] = impulses after sweep it
+  Vel v0 = loadVel(e, 0), v1 = loadVel(e, 1), v2 = loadVel(e, 2);
+  Vel p0 = v0, p1 = v1, p2 = v2, q0 = v0, q1 = v1, q2 = v2;  // after the previous sweep (p) and the one before (q)
+  int result = 0;
+  // Two register copies alternate (no copy between contacts): while `a` is swept, `b` is loaded with the next
+  // constraint, and vice versa.  At the end of a sweep `a` holds constraint 0 again, loaded after its impulses of
+  // this sweep were stored (nvc >= 2 here).
+  VCR a, b;
+  vcrLoad(a, vcs[0]);
+  for (int it = 0; it < velIters; ++it) {
     bool changed = false;
-    for (int k = 0; k < nvc; ++k) {
-      const int bA = vcs[k].bA, bB = vcs[k].bB;
-      Vel A = bA == 0 ? v0 : (bA == 1 ? v1 : (bA == 2 ? v2 : zero));
-      Vel B = bB == 0 ? v0 : (bB == 1 ? v1 : (bB == 2 ? v2 : zero));
-      changed = solveVelocityConstraintCore(vcs[k], A, B) || changed;
-      if (bA == 0) v0 = A; else if (bA == 1) v1 = A; else if (bA == 2) v2 = A;
-      if (bB == 0) v0 = B; else if (bB == 1) v1 = B; else if (bB == 2) v2 = B;
+    float* h = hist[it % 3];
+    for (int k = 0; k < nvc; k += 2) {
+      vcrLoad(b, vcs[k + 1 < nvc ? k + 1 : 0]);  // issued ahead of the arithmetic on `a`
+      changed = vcrStep(a, k, v0, v1, v2, vcs, h) || changed;
+      if (k + 1 < nvc) {
+        vcrLoad(a, vcs[k + 2 < nvc ? k + 2 : 0]);
+        changed = vcrStep(b, k + 1, v0, v1, v2, vcs, h) || changed;
+      } else {
+        a = b;  // odd number of contacts: `b` already holds constraint 0 for the next sweep
+      }
     }
     ++sweeps;
     result = it + 1;
     if (!changed) break;
-    if (it >= kFirstSnap) {
-      SolveSnap& cur = snaps[it % 3];
-      storeVel(e, 0, v0);
-      storeVel(e, 1, v1);
-      storeVel(e, 2, v2);
-      snapSave(e, vcs, nvc, cur);
-      if (it >= kFirstSnap + 2 && snapEqual(cur, snaps[(it + 1) % 3], nvc)) {  // (it - 2) % 3 == (it + 1) % 3
+    if (it >= 2 && velEq(v0, q0) && velEq(v1, q1) && velEq(v2, q2)) {
+      const float* h2 = hist[(it + 1) % 3];  // (it - 2) % 3
+      bool same = true;
+      for (int i = 0; i < 4 * nvc; ++i) same = same && (h[i] == h2[i]);
+      if (same) {  // period-2 cycle: state after sweep it == state after sweep it - 2
         const int remaining = velIters - 1 - it;
         if (remaining & 1) {
-          snapRestore(e, vcs, nvc, snaps[(it + 2) % 3]);                         // (it - 1) % 3
-          v0 = loadVel(e, 0);
-          v1 = loadVel(e, 1);
-          v2 = loadVel(e, 2);
+          const float* h1 = hist[(it + 2) % 3];  // (it - 1) % 3
+          v0 = p0; v1 = p1; v2 = p2;
+          for (int k = 0; k < nvc; ++k) {
+            vcs[k].pt[0].ni = h1[4 * k];
+            vcs[k].pt[0].ti = h1[4 * k + 1];
+            if (vcs[k].count > 1) {
+              vcs[k].pt[1].ni = h1[4 * k + 2];
+              vcs[k].pt[1].ti = h1[4 * k + 3];
+            }
+          }
         }
         break;
       }
     }
+    q0 = p0; q1 = p1; q2 = p2;
+    p0 = v0; p1 = v1; p2 = v2;
     if (it + 1 >= budget && it + 1 < velIters) {
       result = -1;
       break;
@@ -1246,9 +1530,11 @@ HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache&
     initConstraint(S, e, pid, slot, true, &vcs[nvc]);
     ++nvc;
   }
-#if defined(HK_CYCLE_STUDY) && !defined(__CUDA_ARCH__)
-  { extern void studySolve(const Env&, const int*, const VC*, int); studySolve(e, ic, vcs, nvc); }
-#endif
+  {
+    int npts = 0;
+    for (int k = 0; k < nvc; ++k) npts += vcs[k].count;
+    e.dbgShape = (uint32_t)nvc | ((uint32_t)npts << 4);
+  }
   if (nvc > 0) {
     for (int k = 0; k < nvc; ++k) warmStartConstraint(e, vcs[k]);
     int itc = runVelocityIterations(e, vcs, nvc, velIters);

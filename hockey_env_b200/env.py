@@ -267,6 +267,10 @@ class HockeyVecEnv:
                 "sum_episode_len", "touches_p1", "touches_p2", "velocity_iterations", "toi_events", "overflows"]
         return dict(zip(keys, v.tolist()))
 
+    def launches_per_step(self):
+        """Kernels one step() launches (k_fast, k_touch and the general tier(s) of the cascade)."""
+        return int(self.L.hk_launches_per_step(self._h))
+
     def stats_tensor(self):
         """The device accumulators as a float64 tensor view-copy (for an NCCL all-reduce)."""
         t = torch.empty(_lib.STATS_DIM, dtype=torch.float64, device=self.device)

@@ -154,6 +154,11 @@ int hk_copy_stats(hk_env* env, double* dst_dev, void* stream);
 /* Diagnostics: block-cycles the general tiers spent in each tick phase since creation (synchronises the device).
  * out_host8 = tier 1 {policy+Collide, island solve, TOI, finish}, tier 2 {same}. */
 int hk_debug_phase_cycles(hk_env* env, double* out_host8);
+/* Diagnostics (env created with HK_LANE_TRACE=1 in the environment): the last tick's general-tier trace,
+ * [n/32+8 warps][4] cycles per tick phase of each warp, then [n][2] per-env work record (hk_lib.cu). */
+int hk_debug_lane_trace(hk_env* env, uint32_t* out_host, int64_t n_words);
+/* Kernels one hk_step launches on this handle (k_fast, k_touch, general tier(s)); for launch accounting. */
+int hk_launches_per_step(const hk_env* env);
 
 const char* hk_last_error(void);
 const char* hk_version(void);

@@ -32,6 +32,6 @@ for mode, p1, p2 in ((0, 2, 2), (0, 1, 2), (0, 3, 3), (1, 3, 2), (1, 2, 3), (2, 
                 break
     bad_any |= not ok
     total += n * (t + 1)
-    print(f"mode {mode} p1 {names[p1]:6s} p2 {names[p2]:6s} {'ok ' if ok else 'BAD'} tiers(fast/mid/long) {h.fast_counts()}", flush=True)
+    print(f"mode {mode} p1 {names[p1]:6s} p2 {names[p2]:6s} {'ok ' if ok else 'BAD'} tiers(fast/mid/long) {h.fast_counts()} touch {h.touch_count()}", flush=True)
 print(f"{total / 1e6:.2f} M env-steps compared in {time.time() - t0:.0f} s")
 sys.exit(1 if bad_any else 0)

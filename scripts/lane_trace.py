@@ -1,0 +1,39 @@
+"""Diagnostics: which warps / envs form the critical path of the general tier (HK_LANE_TRACE=1)."""
+import os
+import sys
+os.environ["HK_LANE_TRACE"] = "1"
+import numpy as np
+import torch
+sys.path.insert(0, ".")
+import hockey_env_b200 as hk
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+env = hk.HockeyVecEnv(n, device="cuda:0", seed=0, p1="strong", p2="strong")
+env.reset(one_starting=(torch.arange(n, device="cuda:0") % 2).to(torch.int8))
+for _ in range(300):
+    env.step()
+nw = n // 32 + 8
+names = ("policy+collide", "solve", "toi-tasks", "toi-events")
+for rep in range(4):
+    env.step()
+    torch.cuda.synchronize()
+    buf = np.zeros(4 * nw + 2 * n, np.uint32)
+    hk._lib.check(env.L.hk_debug_lane_trace(env._h, buf.ctypes.data, buf.size))
+    w = buf[:4 * nw].reshape(nw, 4).astype(np.int64)
+    rec = buf[4 * nw:].reshape(n, 2)
+    used = rec[:, 0] != 0
+    r0 = rec[used, 0]
+    gw = rec[used, 1]
+    sweeps, toi, kind, shape, ab = r0 & 0xFFF, (r0 >> 12) & 0xF, (r0 >> 16) & 0xF, (r0 >> 20) & 0xFF, r0 >> 31
+    print(f"tick {rep}: general-tier envs {used.sum()}  warps with work {(w.sum(1) > 0).sum()}  aborted {ab.sum()}")
+    tot = w.sum(1)
+    print("  warp cycles: mean", int(tot[tot > 0].mean()), "p50", int(np.percentile(tot[tot > 0], 50)), "p99", int(np.percentile(tot[tot > 0], 99)), "max", int(tot.max()))
+    for k in range(4):
+        c = w[:, k]
+        print(f"  phase {names[k]:15s} mean {int(c[tot > 0].mean()):8d}  p99 {int(np.percentile(c[tot > 0], 99)):8d}  max {int(c.max()):8d}")
+    for k in (1, 3):
+        top = np.argsort(-w[:, k])[:5]
+        for t in top:
+            m = gw == t
+            print(f"    slow {names[k]} warp {t}: {w[t].tolist()} lanes {m.sum()} sweeps {sorted(sweeps[m].tolist())[-4:]} toi {sorted(toi[m].tolist())[-4:]} "
+                  f"shapes(nvc|pts<<4) {sorted(set(shape[m].tolist()))} kinds {sorted(set(kind[m].tolist()))}")

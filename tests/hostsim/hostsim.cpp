@@ -22,7 +22,7 @@ struct HostBatch {
   std::vector<uint32_t> cache;  // [27*6][n]
   double stats[HK_STATS_DIM];
   int use_fast = 0;
-  long long nFast = 0, nSlow = 0, nLong = 0;
+  long long nFast = 0, nSlow = 0, nLong = 0, nTouch = 0;
   int mid_budget = 24;
   Cache cacheOf(int64_t i) { Cache c; c.base = cache.data() + i; c.stride = (size_t)n; return c; }
 };
@@ -67,12 +67,21 @@ void hs_step(void* h, const float* action, int stride, int pol1, int pol2, int f
     groupsToEnv(g, e);
     TickStats st; tickStatsZero(st);
     bool done_fast = false;
+    int bail = 15;
     if (b->use_fast) {
       Env w = e;
       TickStats st2; tickStatsZero(st2);
       if (envTickFast(b->S, b->cfg, w, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st2)) { e = w; st = st2; done_fast = true; }
+      else bail = w.bailKind;
+    }
+    bool done_touch = false;
+    if (b->use_fast && !done_fast && bailClass(bail) == 0) {  // the touch tier (k_touch) takes work class 0 first
+      Env w = e;
+      TickStats st2; tickStatsZero(st2);
+      if (envTickTouch(b->S, b->cfg, b->cacheOf(i), w, (uint64_t)(b->env_id_offset + i), (size_t)i, io, true, st2, nullptr)) { e = w; st = st2; done_touch = true; }
     }
     if (done_fast) b->nFast++;
+    else if (done_touch) b->nTouch++;
     else if (b->use_fast) {
       // the kernel cascade: budgeted middle tier, then the unlimited tier, each from the stored state
       Env w = e;
@@ -88,7 +97,7 @@ void hs_bail_counts(long long* out) { for (int i = 0; i < 16; ++i) out[i] = hk::
 void hs_iter_hist(long long* out) { for (int w = 0; w < 2; ++w) for (int i = 0; i < 182; ++i) out[w * 182 + i] = hk::g_iter_hist[w][i]; for (int i = 0; i < 16; ++i) out[364 + i] = hk::g_period_hist[i]; }
 void hs_toi_dbg(long long* out) { for (int i = 0; i < 16; ++i) out[i] = hk::g_toi_dbg[i]; }
 void hs_set_fast(void* h, int on) { ((HostBatch*)h)->use_fast = on; }
-void hs_fast_counts(void* h, long long* out) { out[0] = ((HostBatch*)h)->nFast; out[1] = ((HostBatch*)h)->nSlow; out[2] = ((HostBatch*)h)->nLong; }
+void hs_fast_counts(void* h, long long* out) { out[0] = ((HostBatch*)h)->nFast; out[1] = ((HostBatch*)h)->nSlow; out[2] = ((HostBatch*)h)->nLong; out[3] = ((HostBatch*)h)->nTouch; }
 void hs_set_mid_budget(void* h, int b) { ((HostBatch*)h)->mid_budget = b; }
 void hs_get_obs(void* h, float* obs, float* obs2) {
   HostBatch* b = (HostBatch*)h;

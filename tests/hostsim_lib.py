@@ -113,9 +113,14 @@ class HostSimBatch:
         self.L.hs_set_obs_state(self.h, _p(s))
 
     def fast_counts(self):
-        c = np.zeros(3, np.int64)
+        c = np.zeros(4, np.int64)
         self.L.hs_fast_counts(self.h, _p(c))
         return int(c[0]), int(c[1]), int(c[2])
+
+    def touch_count(self):
+        c = np.zeros(4, np.int64)
+        self.L.hs_fast_counts(self.h, _p(c))
+        return int(c[3])
 
     def stats(self):
         s = np.zeros(16, np.float64)

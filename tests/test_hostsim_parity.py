@@ -33,7 +33,8 @@ def test_device_code_matches_oracle(oracle, hostsim, mode, p1, p2, fast):
     if fast:
         nfast, nmid, nlong = h.fast_counts()
         assert nfast > 0 and nmid > 0                     # every tier of the cascade was exercised
-        assert nfast + nmid + nlong == 96 * 260
+        assert nfast + nmid + nlong + h.touch_count() == 96 * 260
+        assert h.touch_count() > 0                        # including the touch tier (puck x racket contact ticks)
 
 
 def test_external_actions(oracle, hostsim):

@@ -263,9 +263,21 @@ __global__ void __launch_bounds__(kBlock) k_touch(KParams P, StepIO io) {
 //   TIER == 2 (k_long): unlimited.  Its lanes are the rare long solves and TOI events, packed densely, instead
 //                      of each of them stalling 31 converged neighbours for up to 180 sweeps.
 constexpr int kMidSweeps = 24;
+// one multi-contact velocity solve handed to another lane of the block (phase 2 of k_general)
+struct SolveTask {
+  VC vcs[3];
+  VelTriple v;
+  int result, sweeps;
+};
+constexpr int kSolveSlots = 16;     // tasks per loop shape and block; the rest is solved in place
+constexpr int kTasksPerLane = 3;    // first-pass TOI evaluations a lane may file (phase 3)
+constexpr size_t kRawSolve = sizeof(SolveTask) * HK_SOLVE_KINDS * kSolveSlots;
+constexpr size_t kRawToi = (sizeof(ToiTask) + sizeof(float)) * kSlowBlock * kTasksPerLane;
+constexpr size_t kRawBytes = kRawSolve > kRawToi ? kRawSolve : kRawToi;
 template <int TIER>
-__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass) {
+__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync) {
   __shared__ Scene S;
+  __shared__ __align__(16) unsigned char sRaw[kRawBytes];  // phase 2: SolveTask records; phase 3: TOI tasks + results
   stageScene(&S);
   const int lane = threadIdx.x & 31;
   const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global warp index
@@ -330,18 +342,80 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     worldStepCollide(S, P.cfg, cache, e);
   }
   const long long tw1 = clock64();
-  __syncthreads();
+  // phaseSync bit 0/1/2: block-wide barrier after Collide / after the island solve / after SolveTOI.  They keep the
+  // warps of an SM in the same code region (shared instruction fetch); they are not needed for correctness.
+  if (phaseSync & 1) __syncthreads();
   long long tc1 = clock64();
-  if (valid) solveIslands(S, P.cfg, cache, e, dt, 6 * 30, 2 * 30);  // phase 2
+  // ---- phase 2: island solve.  Velocity iterations of the multi-contact solves (the slowest envs of a tick: they
+  // rarely settle before the 180th sweep) are handed, through shared memory, to one warp per loop shape, so that no
+  // warp has to run several 180-sweep loops one after the other; single-contact solves stay with their lane.
+  IslandCtx ctx;
+  ctx.nvc = 0;
+  if (valid) solveIslandsBegin(S, cache, e, dt, ctx);
+  {
+    SolveTask* tasks = reinterpret_cast<SolveTask*>(sRaw);
+    __shared__ int sKindCount[HK_SOLVE_KINDS];
+    if (threadIdx.x < HK_SOLVE_KINDS) sKindCount[threadIdx.x] = 0;
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5;
+    const int budget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
+    int kind = 0, slot = 0;
+    if (valid && ctx.nvc >= 2) {
+      kind = solveKind(ctx.vcs, ctx.nvc);
+      if (kind > nwarps) kind = 0;
+      if (kind) {
+        slot = atomicAdd(&sKindCount[kind - 1], 1);
+        if (slot >= kSolveSlots) kind = 0;  // no room: solved in place
+      }
+    }
+    if (kind) {
+      SolveTask& t = tasks[(kind - 1) * kSolveSlots + slot];
+      for (int k = 0; k < ctx.nvc; ++k) t.vcs[k] = ctx.vcs[k];
+      t.v.b0 = loadVel(e, 0);
+      t.v.b1 = loadVel(e, 1);
+      t.v.b2 = loadVel(e, 2);
+    }
+    __syncthreads();
+    {
+      const int w = threadIdx.x >> 5;  // warp w runs the loop of shape w + 1
+      if (w < HK_SOLVE_KINDS && lane < min(sKindCount[w], kSolveSlots)) {
+        SolveTask& t = tasks[w * kSolveSlots + lane];
+        VelTriple v = t.v;
+        int sweeps = 0;
+        t.result = runVelocityIterationsKind(w + 1, t.vcs, v, budget, 6 * 30, &sweeps);
+        t.v = v;
+        t.sweeps = sweeps;
+      }
+    }
+    int itc = 0;
+    if (valid && ctx.nvc > 0 && !kind) itc = runVelocityIterations(e, ctx.vcs, ctx.nvc, 6 * 30);
+    __syncthreads();
+    if (kind) {
+      const SolveTask& t = tasks[(kind - 1) * kSolveSlots + slot];
+      for (int k = 0; k < ctx.nvc; ++k) {
+        ctx.vcs[k].pt[0].ni = t.vcs[k].pt[0].ni;
+        ctx.vcs[k].pt[0].ti = t.vcs[k].pt[0].ti;
+        if (ctx.vcs[k].count == 2) {
+          ctx.vcs[k].pt[1].ni = t.vcs[k].pt[1].ni;
+          ctx.vcs[k].pt[1].ti = t.vcs[k].pt[1].ti;
+        }
+      }
+      storeVel(e, 0, t.v.b0);
+      storeVel(e, 1, t.v.b1);
+      storeVel(e, 2, t.v.b2);
+      e.nVelIters += (uint32_t)t.sweeps;
+      itc = t.result;
+    }
+    if (valid) solveIslandsEnd(S, e, dt, 2 * 30, ctx, itc);
+  }
   const long long tw2 = clock64();
-  __syncthreads();
+  if (phaseSync & 2) __syncthreads();
   long long tc2 = clock64();
   // phase 3a-3c: first-pass TOI evaluations of the whole block as one task list, one task per thread
   const bool wantToi = valid && !e.aborted && (e.exist & HK_PAIRS_TOI);
   {
-    constexpr int kTasksPerLane = 3;
-    __shared__ ToiTask sTasks[kSlowBlock * kTasksPerLane];  // worst case: every lane files all its tasks
-    __shared__ float sAlpha[kSlowBlock * kTasksPerLane];
+    ToiTask* sTasks = reinterpret_cast<ToiTask*>(sRaw);  // worst case: every lane files all its tasks
+    float* sAlpha = reinterpret_cast<float*>(sRaw + sizeof(ToiTask) * kSlowBlock * kTasksPerLane);
     __shared__ int sCount;
     if (threadIdx.x == 0) sCount = 0;
     __syncthreads();
@@ -376,9 +450,9 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     w[2] = (uint32_t)(tw3a - tc2);
     w[3] = (uint32_t)(tw3 - tw3a);
   }
-  __syncthreads();
+  if (phaseSync & 4) __syncthreads();
   long long tc3 = clock64();
-  {  // diagnostics: block-wide max of per-lane TOI evaluation / event cycles
+  if (phaseSync & 4) {  // diagnostics: block-wide max of per-lane TOI evaluation / event cycles
     __shared__ unsigned long long sMaxEval, sMaxEvent;
     if (threadIdx.x == 0) { sMaxEval = 0; sMaxEvent = 0; }
     __syncthreads();
@@ -582,6 +656,7 @@ struct hk_env {
   }
   int lanes1, lanes2;  // log2 envs per warp in tier 1 / tier 2 (HK_LANES1 / HK_LANES2 override)
   bool touch;          // HK_TOUCH=0 disables the touch tier (A/B measurements)
+  int phaseSync;       // HK_PHASE_SYNC: which phase barriers the general tiers keep (bit mask, see k_general)
   int launches;        // kernels per tick of the cascade
   // one tick: k_fast over all envs, k_touch over work class 0, the general tier(s) over the rest
   void launchCascade(const StepIO& io, cudaStream_t stream) const {
@@ -589,8 +664,8 @@ struct hk_env {
     k_fast<<<grid(), kBlock, 0, stream>>>(params(), io);
     if (touch) k_touch<<<grid(), kBlock, 0, stream>>>(params(), io);
     const int b1 = blockFor(touch ? 0.15 : 0.75), b2 = blockFor(0.06);
-    k_general<1><<<gridSlow(lanes1, b1), b1, 0, stream>>>(params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0);
-    if (tiers == 3) k_general<2><<<gridSlow(lanes2, b2), b2, 0, stream>>>(params(), io, 1, lanes2, 0);
+    k_general<1><<<gridSlow(lanes1, b1), b1, 0, stream>>>(params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync);
+    if (tiers == 3) k_general<2><<<gridSlow(lanes2, b2), b2, 0, stream>>>(params(), io, 1, lanes2, 0, phaseSync);
   }
 };
 
@@ -648,6 +723,8 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     const char* tt = getenv("HK_TOUCH");
     h->touch = n_envs >= 200000;
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
+    h->phaseSync = 7;
+    if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 7;
     h->launches = h->mono ? 1 : 2 + (h->touch ? 1 : 0) + (h->tiers == 3 ? 1 : 0);
   }
   Scene S;

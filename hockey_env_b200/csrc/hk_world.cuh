@@ -1170,17 +1170,30 @@ HK_HD bool vcrStep(VCR& c, int k, Vel& v0, Vel& v1, Vel& v2, VC* vcs, float* h) 
 struct VelTriple {
   Vel b0, b1, b2;
 };
+HK_HD float sel3(bool p0, bool p1, bool p2, float x0, float x1, float x2) { return p0 ? x0 : (p1 ? x1 : (p2 ? x2 : 0.0f)); }
+// sweep constraint c against the three register-resident body velocities: the two bodies it couples are picked
+// and written back with scalar selects (no branches; bA != bB, and -1 = static reads as zero and is never written)
 template <int COUNT>
 HK_HD bool vcrStepR(VCR& c, VelTriple& v) {
-  Vel zero;
-  zero.v = mk(0.0f, 0.0f);
-  zero.w = 0.0f;
-  const int bA = c.bA, bB = c.bB;
-  Vel A = bA == 0 ? v.b0 : (bA == 1 ? v.b1 : (bA == 2 ? v.b2 : zero));
-  Vel B = bB == 0 ? v.b0 : (bB == 1 ? v.b1 : (bB == 2 ? v.b2 : zero));
+  const bool a0 = c.bA == 0, a1 = c.bA == 1, a2 = c.bA == 2;
+  const bool b0 = c.bB == 0, b1 = c.bB == 1, b2 = c.bB == 2;
+  Vel A, B;
+  A.v.x = sel3(a0, a1, a2, v.b0.v.x, v.b1.v.x, v.b2.v.x);
+  A.v.y = sel3(a0, a1, a2, v.b0.v.y, v.b1.v.y, v.b2.v.y);
+  A.w = sel3(a0, a1, a2, v.b0.w, v.b1.w, v.b2.w);
+  B.v.x = sel3(b0, b1, b2, v.b0.v.x, v.b1.v.x, v.b2.v.x);
+  B.v.y = sel3(b0, b1, b2, v.b0.v.y, v.b1.v.y, v.b2.v.y);
+  B.w = sel3(b0, b1, b2, v.b0.w, v.b1.w, v.b2.w);
   const bool changed = vcrSweep<COUNT>(c, A, B);
-  if (bA == 0) v.b0 = A; else if (bA == 1) v.b1 = A; else if (bA == 2) v.b2 = A;
-  if (bB == 0) v.b0 = B; else if (bB == 1) v.b1 = B; else if (bB == 2) v.b2 = B;
+  v.b0.v.x = a0 ? A.v.x : (b0 ? B.v.x : v.b0.v.x);
+  v.b0.v.y = a0 ? A.v.y : (b0 ? B.v.y : v.b0.v.y);
+  v.b0.w = a0 ? A.w : (b0 ? B.w : v.b0.w);
+  v.b1.v.x = a1 ? A.v.x : (b1 ? B.v.x : v.b1.v.x);
+  v.b1.v.y = a1 ? A.v.y : (b1 ? B.v.y : v.b1.v.y);
+  v.b1.w = a1 ? A.w : (b1 ? B.w : v.b1.w);
+  v.b2.v.x = a2 ? A.v.x : (b2 ? B.v.x : v.b2.v.x);
+  v.b2.v.y = a2 ? A.v.y : (b2 ? B.v.y : v.b2.v.y);
+  v.b2.w = a2 ? A.w : (b2 ? B.w : v.b2.w);
   return changed;
 }
 struct Imp4 {
@@ -1207,20 +1220,17 @@ HK_HD void vcrStoreImpulses(const VCR& c, VC& m) {
     m.pt[1].ti = c.ti1;
   }
 }
+// `vcs` may live anywhere (the caller's local array, or a block-shared task record another lane filled in: hk_lib.cu
+// hands the multi-contact solves of a block to warps that each run ONE loop shape)
 template <int C0, int C1, int C2>  // C2 == 0: two contacts
-HK_HD_NOINLINE int runVelocityIterationsFixed(Env& e, VC* vcs, int velIters) {
-  const int budget = e.sweepBudget;
+HK_HD_NOINLINE int runVelocityIterationsFixedCore(VC* vcs, VelTriple& vio, int budget, int velIters, int* sweepsOut) {
   int sweeps = 0;
+  VelTriple v = vio;  // registers for the whole loop
   VCR a, b, c;
   vcrLoad(a, vcs[0]);
   vcrLoad(b, vcs[1]);
   if (C2 != 0) vcrLoad(c, vcs[2]);
-  VelTriple v, p, q;  // now, after the previous sweep, after the one before
-  v.b0 = loadVel(e, 0);
-  v.b1 = loadVel(e, 1);
-  v.b2 = loadVel(e, 2);
-  p = v;
-  q = v;
+  VelTriple p = v, q = v;  // after the previous sweep, after the one before
   Imp4 pa = impOf(a), pb = impOf(b), pc = impOf(C2 != 0 ? c : a), qa = pa, qb = pb, qc = pc;
   int result = 0;
   for (int it = 0; it < velIters; ++it) {
@@ -1256,26 +1266,45 @@ HK_HD_NOINLINE int runVelocityIterationsFixed(Env& e, VC* vcs, int velIters) {
   vcrStoreImpulses(a, vcs[0]);
   vcrStoreImpulses(b, vcs[1]);
   if (C2 != 0) vcrStoreImpulses(c, vcs[2]);
-  storeVel(e, 0, v.b0);
-  storeVel(e, 1, v.b1);
-  storeVel(e, 2, v.b2);
-  e.nVelIters += (uint32_t)sweeps;
+  vio = v;
+  *sweepsOut = sweeps;
   return result;
+}
+// shape of a multi-contact solve that has a fixed-shape loop: 1..4 = two contacts with (1,1) (1,2) (2,1) (2,2)
+// manifold points, 5 = three single-point contacts, 0 = none (one contact, or anything larger: general loop)
+enum { HK_SOLVE_KINDS = 5 };
+HK_HD int solveKind(const VC* vcs, int nvc) {
+  if (nvc == 2) return 1 + (vcs[0].count - 1) * 2 + (vcs[1].count - 1);
+  if (nvc == 3 && vcs[0].count == 1 && vcs[1].count == 1 && vcs[2].count == 1) return 5;
+  return 0;
+}
+HK_HD int runVelocityIterationsKind(int kind, VC* vcs, VelTriple& v, int budget, int velIters, int* sweepsOut) {
+  switch (kind) {
+    case 1: return runVelocityIterationsFixedCore<1, 1, 0>(vcs, v, budget, velIters, sweepsOut);
+    case 2: return runVelocityIterationsFixedCore<1, 2, 0>(vcs, v, budget, velIters, sweepsOut);
+    case 3: return runVelocityIterationsFixedCore<2, 1, 0>(vcs, v, budget, velIters, sweepsOut);
+    case 4: return runVelocityIterationsFixedCore<2, 2, 0>(vcs, v, budget, velIters, sweepsOut);
+    default: return runVelocityIterationsFixedCore<1, 1, 1>(vcs, v, budget, velIters, sweepsOut);
+  }
 }
 
 // returns the number of sweeps executed, or -1 if the tier's sweep budget ran out before the state repeated
 HK_HD_NOINLINE int runVelocityIterations(Env& e, VC* vcs, int nvc, int velIters) {
   if (nvc == 1 && vcs[0].count == 1) return runVelocityIterations1(e, vcs[0], velIters);
   if (nvc == 1 && vcs[0].count == 2) return runVelocityIterations2(e, vcs[0], velIters);
-  if (nvc == 2) {
-    const int c0 = vcs[0].count, c1 = vcs[1].count;
-    if (c0 == 1 && c1 == 1) return runVelocityIterationsFixed<1, 1, 0>(e, vcs, velIters);
-    if (c0 == 1 && c1 == 2) return runVelocityIterationsFixed<1, 2, 0>(e, vcs, velIters);
-    if (c0 == 2 && c1 == 1) return runVelocityIterationsFixed<2, 1, 0>(e, vcs, velIters);
-    return runVelocityIterationsFixed<2, 2, 0>(e, vcs, velIters);
+  if (const int kind = solveKind(vcs, nvc)) {
+    VelTriple v;
+    v.b0 = loadVel(e, 0);
+    v.b1 = loadVel(e, 1);
+    v.b2 = loadVel(e, 2);
+    int sweeps = 0;
+    const int result = runVelocityIterationsKind(kind, vcs, v, e.sweepBudget, velIters, &sweeps);
+    storeVel(e, 0, v.b0);
+    storeVel(e, 1, v.b1);
+    storeVel(e, 2, v.b2);
+    e.nVelIters += (uint32_t)sweeps;
+    return result;
   }
-  if (nvc == 3 && vcs[0].count == 1 && vcs[1].count == 1 && vcs[2].count == 1)
-    return runVelocityIterationsFixed<1, 1, 1>(e, vcs, velIters);
   const int budget = e.sweepBudget;
   int sweeps = 0;
   float hist[3][MAX_MANIFOLDS * 4];  // [it % 3] = impulses after sweep it
@@ -1435,14 +1464,24 @@ HK_HD_NOINLINE void synchronizeFixturesQ0(const Scene& S, Env& e, int bi, Rot q0
   moveProxy(e, bi, comb, b.p - xf1.p);
 }
 
-HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h, int velIters, int posIters) {
-  (void)cfg;
+// what the first half of the island solve (islands, velocity integration, constraint setup, warm start) leaves for
+// the velocity iterations and the second half (position iterations, sleeping, proxies)
+struct IslandCtx {
+  int ic[MAX_MANIFOLDS];  // island contacts in solver order
+  unsigned char icIsl[MAX_MANIFOLDS];
+  uint32_t islBodies[3];
+  int nIsl;
+  Rot q0[3];
+  int nvc;
+  VC vcs[MAX_MANIFOLDS];
+};
+HK_HD_NOINLINE void solveIslandsBegin(const Scene& S, const Cache& cache, Env& e, float h, IslandCtx& ctx) {
   e.b[0].island = e.b[1].island = e.b[2].island = false;
   uint32_t inIsland = 0;  // contacts
-  int ic[MAX_MANIFOLDS];          // island contacts in solver order
-  unsigned char icIsl[MAX_MANIFOLDS];
+  int* ic = ctx.ic;
+  unsigned char* icIsl = ctx.icIsl;
   int nic = 0;
-  uint32_t islBodies[3];
+  uint32_t* islBodies = ctx.islBodies;
   int nIsl = 0;
   for (int seed = 2; seed >= 0; --seed) {
     if (e.b[seed].island) continue;
@@ -1483,8 +1522,9 @@ HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache&
     }
     islBodies[nIsl++] = bm;
   }
+  ctx.nIsl = nIsl;
   // ---- integrate velocities (b2Island::Solve, first loop) ----
-  Rot q0[3];
+  Rot* q0 = ctx.q0;
   for (int bi = 0; bi < 3; ++bi) {
     Body& b = e.b[bi];
     q0[bi] = b.q;
@@ -1497,7 +1537,7 @@ HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache&
     b.w *= fclamp(1.0f - h * b.adamp, 0.0f, 1.0f);
   }
   // ---- constraints ----
-  VC vcs[MAX_MANIFOLDS];
+  VC* vcs = ctx.vcs;
   int nvc = 0;
   for (int k = 0; k < nic; ++k) {
     int pid = ic[k];
@@ -1535,9 +1575,18 @@ HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache&
     for (int k = 0; k < nvc; ++k) npts += vcs[k].count;
     e.dbgShape = (uint32_t)nvc | ((uint32_t)npts << 4);
   }
+  ctx.nvc = nvc;
+  for (int k = 0; k < nvc; ++k) warmStartConstraint(e, vcs[k]);
+}
+// itc = what the velocity iterations over ctx.vcs returned (ignored when there are no constraints)
+HK_HD_NOINLINE void solveIslandsEnd(const Scene& S, Env& e, float h, int posIters, IslandCtx& ctx, int itc) {
+  const int nvc = ctx.nvc, nIsl = ctx.nIsl;
+  VC* vcs = ctx.vcs;
+  const int* ic = ctx.ic;
+  const unsigned char* icIsl = ctx.icIsl;
+  const uint32_t* islBodies = ctx.islBodies;
+  const Rot* q0 = ctx.q0;
   if (nvc > 0) {
-    for (int k = 0; k < nvc; ++k) warmStartConstraint(e, vcs[k]);
-    int itc = runVelocityIterations(e, vcs, nvc, velIters);
     if (itc < 0) {
       e.aborted = true;
       return;
@@ -1606,6 +1655,13 @@ HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache&
   for (int bi = 2; bi >= 0; --bi)
     if (e.b[bi].island) synchronizeFixturesQ0(S, e, bi, q0[bi]);
   findNewContacts(S, e);
+}
+HK_HD_NOINLINE void solveIslands(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h, int velIters, int posIters) {
+  (void)cfg;
+  IslandCtx ctx;
+  solveIslandsBegin(S, cache, e, h, ctx);
+  const int itc = ctx.nvc > 0 ? runVelocityIterations(e, ctx.vcs, ctx.nvc, velIters) : 0;
+  solveIslandsEnd(S, e, h, posIters, ctx, itc);
 }
 
 // ---- b2World::SolveTOI: continuous collision of the dynamic bodies against the statics ---------------

@@ -1,16 +1,20 @@
-"""Turns gpurun_out/r1_final_full.ncu-rep (+ launch list, bench JSONs) into the small tracked files under profiles/.
-Run in the build container (ncu can read reports without a GPU):  python scripts/extract_profiles.py"""
+"""Turns gpurun_out/<tag>_full.ncu-rep (+ launch list, bench JSONs) into the small tracked files under profiles/.
+Run in the build container (ncu can read reports without a GPU):  python scripts/extract_profiles.py [tag]
+(tag = r1_final (default), r1b, ...: the capture set of one gpurun evidence call)"""
 import bisect
 import csv
 import os
 import re
 import shutil
 import subprocess
+import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
-REP = os.path.join(OUT, "r1_final_full.ncu-rep")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1_final"
+SHORT = TAG.replace("_final", "")  # bench_<short>_*.json
+REP = os.path.join(OUT, TAG + "_full.ncu-rep")
 csv.field_size_limit(10 ** 9)
 
 
@@ -20,9 +24,11 @@ def ncu(*args):
 
 def main():
     os.makedirs(PROF, exist_ok=True)
-    for src, dst in (("r1_final_launches.csv", "r1_final_launches.csv"), ("bench_r1_final.json", "r1_bench_1gpu.json"),
-                     ("bench_r1_1M.json", "r1_bench_1gpu_1M_envs.json"), ("bench_r1_2gpu.json", "r1_bench_2gpu.json"),
-                     ("bench_r1_ref.json", "r1_bench_reference_arm.json"), ("phase_cycles.txt", "r1_phase_cycles.txt")):
+    pc = "phase_cycles.txt" if TAG == "r1_final" else "phase_cycles_%s.txt" % SHORT
+    for src, dst in ((TAG + "_launches.csv", TAG + "_launches.csv"), ("bench_%s_final.json" % SHORT, SHORT + "_bench_1gpu.json"),
+                     ("bench_%s_131k.json" % SHORT, SHORT + "_bench_1gpu_131k_envs.json"),
+                     ("bench_%s_1M.json" % SHORT, SHORT + "_bench_1gpu_1M_envs.json"), ("bench_%s_2gpu.json" % SHORT, SHORT + "_bench_2gpu.json"),
+                     ("bench_%s_ref.json" % SHORT, SHORT + "_bench_reference_arm.json"), (pc, SHORT + "_phase_cycles.txt")):
         if os.path.exists(os.path.join(OUT, src)):
             shutil.copy(os.path.join(OUT, src), os.path.join(PROF, dst))
     rows = list(csv.reader(ncu("--page", "raw", "--csv").splitlines()))
@@ -34,7 +40,7 @@ def main():
             "gpu__dram_throughput", "sm__inst_executed_pipe_fp64", "smsp__inst_executed_op_local", "sm__cycles_elapsed.max",
             "smsp__cycles_active.avg", "l1tex__t_bytes_pipe_lsu_mem_local")
     keep = [i for i, h in enumerate(hdr) if h in ("Block Size", "Grid Size") or h.startswith(pref)]
-    with open(os.path.join(PROF, "r1_final_raw_metrics.csv"), "w", newline="") as f:
+    with open(os.path.join(PROF, TAG + "_raw_metrics.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["metric", "unit"] + [r[hdr.index("Kernel Name")][:44] for r in rows[2:]])
         for i in keep:
@@ -70,7 +76,7 @@ def main():
 
     csrc = os.path.join(ROOT, "hockey_env_b200", "csrc")
     fmap = {f: funcs(os.path.join(csrc, f)) for f in os.listdir(csrc)}
-    with open(os.path.join(PROF, "r1_final_hotspots_by_function.csv"), "w", newline="") as f:
+    with open(os.path.join(PROF, TAG + "_hotspots_by_function.csv"), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["kernel", "file", "function", "pct_warp_instructions", "pct_stall_samples", "active_threads_per_instruction"])
         for kern, agg in data.items():

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_PKG, "libhockey_b200.so")
+SO_PATH = os.environ.get("HK_LIB_PATH") or os.path.join(_PKG, "libhockey_b200.so")  # override: A/B of builds only
 
 OBS_DIM, ACT_DIM, INFO_DIM, STATS_DIM = 18, 4, 4, 16
 N_PAIRS, CONTACT_WORDS = 27, 8

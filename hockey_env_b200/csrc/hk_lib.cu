@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 
 #include "../../include/hockey_b200.h"
@@ -112,7 +113,7 @@ struct KParams {
   uint32_t* qctl;    // queue counters, see Q_* below
   unsigned long long* phaseClk;  // [2 tiers][4 phases] block-cycles spent per phase (diagnostics, hk_debug_phase_cycles)
   float* actBuf;     // [n,8] actions handed from k_fast to the general tiers
-  uint32_t* trace;   // diagnostics (HK_LANE_TRACE=1): [n/32+8 warps][4] phase cycles, then [n][2] per-env work record
+  uint32_t* trace;   // diagnostics (HK_LANE_TRACE=1): [n/32+8 warps][4] phase cycles, [n][2] per-env work record, [n/32+8 blocks][12] block stamps
   int64_t n;
   int64_t env_id_offset;
   Config cfg;
@@ -263,28 +264,46 @@ __global__ void __launch_bounds__(kBlock) k_touch(KParams P, StepIO io) {
 //   TIER == 2 (k_long): unlimited.  Its lanes are the rare long solves and TOI events, packed densely, instead
 //                      of each of them stalling 31 converged neighbours for up to 180 sweeps.
 constexpr int kMidSweeps = 24;
-// one multi-contact velocity solve handed to another lane of the block (phase 2 of k_general)
-struct SolveTask {
+// Velocity solves of a block are pooled in shared memory (phase 2 of k_general) and dealt to its warps as units of one
+// loop shape each: a warp never runs two different 180-sweep loops one after the other unless the block holds more
+// units than warps, and the lanes of a unit all execute the same register-resident loop.
+struct SolveTask {   // multi-contact solve with a fixed-shape loop (solveKind 1..5)
   VC vcs[3];
   VelTriple v;
   int result, sweeps;
 };
-constexpr int kSolveSlots = 16;     // tasks per loop shape and block; the rest is solved in place
+struct Solve1Task {  // one contact, one or two manifold points
+  VC vc;
+  Vel A, B;
+  int result, sweeps;
+};
+enum { HK_MULTI_KINDS = 5 };
+constexpr int kSolveSlots = 12;     // multi-contact tasks per loop shape and block; the rest is solved in place
 constexpr int kTasksPerLane = 3;    // first-pass TOI evaluations a lane may file (phase 3)
-constexpr size_t kRawSolve = sizeof(SolveTask) * HK_SOLVE_KINDS * kSolveSlots;
-constexpr size_t kRawToi = (sizeof(ToiTask) + sizeof(float)) * kSlowBlock * kTasksPerLane;
-constexpr size_t kRawBytes = kRawSolve > kRawToi ? kRawSolve : kRawToi;
+constexpr size_t kRawMulti = sizeof(SolveTask) * HK_MULTI_KINDS * kSolveSlots;
+__host__ __device__ constexpr size_t rawBytes(int envLanes) {  // dynamic shared memory of k_general for envLanes env lanes
+  const size_t solve = kRawMulti + sizeof(Solve1Task) * (size_t)envLanes;
+  const size_t toi = (sizeof(ToiTask) + sizeof(float)) * (size_t)envLanes * kTasksPerLane;
+  return solve > toi ? solve : toi;
+}
 template <int TIER>
-__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync) {
+__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync, int envWarps) {
   __shared__ Scene S;
-  __shared__ __align__(16) unsigned char sRaw[kRawBytes];  // phase 2: SolveTask records; phase 3: TOI tasks + results
+  extern __shared__ __align__(16) unsigned char sRaw[];  // phase 2: solve tasks; phase 3: TOI tasks + results (rawBytes())
   stageScene(&S);
   const int lane = threadIdx.x & 31;
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // global warp index
+  // The first envWarps warps of a block carry envs; the others are helpers that only take part in the pooled phases
+  // (velocity solves, TOI evaluations).  A small batch leaves most of an SM's issue slots idle: helpers let its
+  // pooled work spread over more warps than it has env warps.
+  const int wib = threadIdx.x >> 5;
+  const bool envWarp = wib < envWarps;
+  const int64_t gw = (int64_t)blockIdx.x * envWarps + wib;  // global env-warp index (env warps only)
+  const int envLanes = envWarps << 5;
   // Only the first `lanes` lanes of a warp carry an env.  With small batches the general tiers are bound by
   // per-warp latency (instruction fetch, local memory), not by issue slots: fewer envs per warp means fewer
   // distinct control-flow paths to serialise and more warps in flight to hide the latency.
-  const int lanes = 1 << lanesLog2;
+  // lanesLog2 packs log2(envs per warp) of the four work classes, 3 bits each (tier 2: class 0's value)
+  int cls = 0;
   bool valid = false;
   int64_t i = 0;
   if (TIER == 1) {
@@ -292,11 +311,13 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
 #pragma unroll
     for (int c = 0; c < Q_CLASSES; ++c) {
       const unsigned cnt = c < firstClass ? 0u : *((volatile uint32_t*)&P.qctl[c]);  // class 0 was k_touch's
-      const int64_t nw = ((int64_t)cnt + lanes - 1) >> lanesLog2;
-      if (!valid && gw >= w0 && gw < w0 + nw && lane < lanes) {
-        const int64_t j = ((gw - w0) << lanesLog2) + lane;
+      const int ll = (lanesLog2 >> (3 * c)) & 7, lanes = 1 << ll;
+      const int64_t nw = ((int64_t)cnt + lanes - 1) >> ll;
+      if (envWarp && !valid && gw >= w0 && gw < w0 + nw && lane < lanes) {
+        const int64_t j = ((gw - w0) << ll) + lane;
         if (j < (int64_t)cnt) {
           valid = true;
+          cls = c;
           i = P.queue[(int64_t)c * P.n + j];
         }
       }
@@ -304,8 +325,9 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     }
   } else {
     const unsigned cnt = *((volatile uint32_t*)&P.qctl[QC_COUNT2]);
-    const int64_t j = (gw << lanesLog2) + lane;
-    if (lane < lanes && j < (int64_t)cnt) {
+    const int ll = lanesLog2 & 7, lanes = 1 << ll;
+    const int64_t j = (gw << ll) + lane;
+    if (envWarp && lane < lanes && j < (int64_t)cnt) {
       valid = true;
       i = P.queue[(int64_t)Q_CLASSES * P.n + j];
     }
@@ -346,30 +368,40 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   // warps of an SM in the same code region (shared instruction fetch); they are not needed for correctness.
   if (phaseSync & 1) __syncthreads();
   long long tc1 = clock64();
-  // ---- phase 2: island solve.  Velocity iterations of the multi-contact solves (the slowest envs of a tick: they
-  // rarely settle before the 180th sweep) are handed, through shared memory, to one warp per loop shape, so that no
-  // warp has to run several 180-sweep loops one after the other; single-contact solves stay with their lane.
+  // ---- phase 2: island solve.  The velocity iterations of the whole block are pooled (see SolveTask): every lane files
+  // its solve by loop shape, the warps of the block (helpers included) take one unit of one shape at a time.
   IslandCtx ctx;
   ctx.nvc = 0;
+  long long stampB = 0, stampV = 0, stampT = 0;  // diagnostics: block-level stamps inside phases 2 and 3
   if (valid) solveIslandsBegin(S, cache, e, dt, ctx);
   {
-    SolveTask* tasks = reinterpret_cast<SolveTask*>(sRaw);
-    __shared__ int sKindCount[HK_SOLVE_KINDS];
-    if (threadIdx.x < HK_SOLVE_KINDS) sKindCount[threadIdx.x] = 0;
+    SolveTask* mtasks = reinterpret_cast<SolveTask*>(sRaw);
+    Solve1Task* stasks = reinterpret_cast<Solve1Task*>(sRaw + kRawMulti);  // 1-point tasks from the front, 2-point from the back
+    __shared__ int sKindCount[HK_MULTI_KINDS + 2];  // [0..4] multi kinds 1..5, [5] one contact x 1 point, [6] one contact x 2 points
+    if (threadIdx.x < HK_MULTI_KINDS + 2) sKindCount[threadIdx.x] = 0;
     __syncthreads();
+    stampB = clock64();
     const int nwarps = blockDim.x >> 5;
     const int budget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
-    int kind = 0, slot = 0;
+    const bool pool1 = (phaseSync & 8) != 0;  // also pool the single-contact solves
+    int kind = 0, slot = 0;  // kind 1..5: multi; 6: single contact, 1 point; 7: single contact, 2 points
     if (valid && ctx.nvc >= 2) {
       kind = solveKind(ctx.vcs, ctx.nvc);
-      if (kind > nwarps) kind = 0;
       if (kind) {
         slot = atomicAdd(&sKindCount[kind - 1], 1);
         if (slot >= kSolveSlots) kind = 0;  // no room: solved in place
       }
+    } else if (valid && ctx.nvc == 1 && pool1) {
+      kind = 5 + ctx.vcs[0].count;
+      slot = atomicAdd(&sKindCount[kind - 1], 1);
     }
-    if (kind) {
-      SolveTask& t = tasks[(kind - 1) * kSolveSlots + slot];
+    if (kind >= 6) {
+      Solve1Task& t = stasks[kind == 6 ? slot : envLanes - 1 - slot];
+      t.vc = ctx.vcs[0];
+      t.A = loadVel(e, ctx.vcs[0].bA);
+      t.B = loadVel(e, ctx.vcs[0].bB);
+    } else if (kind) {
+      SolveTask& t = mtasks[(kind - 1) * kSolveSlots + slot];
       for (int k = 0; k < ctx.nvc; ++k) t.vcs[k] = ctx.vcs[k];
       t.v.b0 = loadVel(e, 0);
       t.v.b1 = loadVel(e, 1);
@@ -377,21 +409,76 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     }
     __syncthreads();
     {
-      const int w = threadIdx.x >> 5;  // warp w runs the loop of shape w + 1
-      if (w < HK_SOLVE_KINDS && lane < min(sKindCount[w], kSolveSlots)) {
-        SolveTask& t = tasks[w * kSolveSlots + lane];
-        VelTriple v = t.v;
-        int sweeps = 0;
-        t.result = runVelocityIterationsKind(w + 1, t.vcs, v, budget, 6 * 30, &sweeps);
-        t.v = v;
-        t.sweeps = sweeps;
+      // unit list, identical in every warp: the multi-contact shapes that have tasks (heaviest loops first), then the
+      // 2-point chunks, then the 1-point chunks; spare warps split the 1-point tasks into smaller chunks
+      const int n1 = sKindCount[5], n2 = sKindCount[6];
+      int nm = 0, mk_[HK_MULTI_KINDS];
+#pragma unroll
+      for (int q = 0; q < HK_MULTI_KINDS; ++q) {
+        const int k = q == 0 ? 4 : (q == 1 ? 2 : (q == 2 ? 3 : (q == 3 ? 5 : 1)));
+        if (sKindCount[k - 1] > 0) mk_[nm++] = k;
+      }
+      const int c2 = (n2 + 31) >> 5;
+      int c1 = (n1 + 31) >> 5;
+      const int spare = nwarps - nm - c2;
+      if (spare > c1) c1 = min(spare, (n1 + 3) >> 2);
+      const int units = nm + c2 + c1;
+      for (int u = wib; u < units; u += nwarps) {
+        if (u < nm) {
+          const int k = mk_[u];
+          if (lane < min(sKindCount[k - 1], kSolveSlots)) {
+            SolveTask& t = mtasks[(k - 1) * kSolveSlots + lane];
+            VelTriple v = t.v;
+            int sweeps = 0;
+            t.result = runVelocityIterationsKind(k, t.vcs, v, budget, 6 * 30, &sweeps);
+            t.v = v;
+            t.sweeps = sweeps;
+          }
+        } else if (u < nm + c2) {
+          const int j = ((u - nm) << 5) + lane;
+          if (j < n2) {
+            Solve1Task& t = stasks[envLanes - 1 - j];
+            Vel A = t.A, B = t.B;
+            int sweeps = 0;
+            t.result = runVelocityIterations2Core(t.vc, A, B, budget, 6 * 30, &sweeps);
+            t.A = A;
+            t.B = B;
+            t.sweeps = sweeps;
+          }
+        } else {
+          const int c = u - nm - c2;
+          const int lo = (int)(((long long)n1 * c) / c1), hi = (int)(((long long)n1 * (c + 1)) / c1);
+          const int j = lo + lane;
+          if (j < hi) {
+            Solve1Task& t = stasks[j];
+            Vel A = t.A, B = t.B;
+            int sweeps = 0;
+            t.result = runVelocityIterations1Core(t.vc, A, B, budget, 6 * 30, &sweeps);
+            t.A = A;
+            t.B = B;
+            t.sweeps = sweeps;
+          }
+        }
       }
     }
     int itc = 0;
     if (valid && ctx.nvc > 0 && !kind) itc = runVelocityIterations(e, ctx.vcs, ctx.nvc, 6 * 30);
     __syncthreads();
-    if (kind) {
-      const SolveTask& t = tasks[(kind - 1) * kSolveSlots + slot];
+    stampV = clock64();
+    if (kind >= 6) {
+      const Solve1Task& t = stasks[kind == 6 ? slot : envLanes - 1 - slot];
+      ctx.vcs[0].pt[0].ni = t.vc.pt[0].ni;
+      ctx.vcs[0].pt[0].ti = t.vc.pt[0].ti;
+      if (kind == 7) {
+        ctx.vcs[0].pt[1].ni = t.vc.pt[1].ni;
+        ctx.vcs[0].pt[1].ti = t.vc.pt[1].ti;
+      }
+      storeVel(e, ctx.vcs[0].bA, t.A);
+      storeVel(e, ctx.vcs[0].bB, t.B);
+      e.nVelIters += (uint32_t)t.sweeps;
+      itc = t.result;
+    } else if (kind) {
+      const SolveTask& t = mtasks[(kind - 1) * kSolveSlots + slot];
       for (int k = 0; k < ctx.nvc; ++k) {
         ctx.vcs[k].pt[0].ni = t.vcs[k].pt[0].ni;
         ctx.vcs[k].pt[0].ti = t.vcs[k].pt[0].ti;
@@ -415,7 +502,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   const bool wantToi = valid && !e.aborted && (e.exist & HK_PAIRS_TOI);
   {
     ToiTask* sTasks = reinterpret_cast<ToiTask*>(sRaw);  // worst case: every lane files all its tasks
-    float* sAlpha = reinterpret_cast<float*>(sRaw + sizeof(ToiTask) * kSlowBlock * kTasksPerLane);
+    float* sAlpha = reinterpret_cast<float*>(sRaw + sizeof(ToiTask) * (size_t)envLanes * kTasksPerLane);
     __shared__ int sCount;
     if (threadIdx.x == 0) sCount = 0;
     __syncthreads();
@@ -435,6 +522,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     const int nwarps = blockDim.x >> 5;
     for (int t = lane * nwarps + (threadIdx.x >> 5); t < total; t += blockDim.x) sAlpha[t] = toiTaskRun(S, sTasks[t]);
     __syncthreads();
+    stampT = clock64();
     for (int k = 0; k < nMine; ++k) {
       e.toiPre[mine[k].pid] = sAlpha[base + k];
       e.toiPreFlag |= 1u << mine[k].pid;
@@ -443,7 +531,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   const long long tw3a = clock64();
   if (wantToi) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3d: events (rare) on top of the pre-seeded results
   const long long tw3 = clock64();
-  if (P.trace && TIER == 1 && lane == 0 && gw < P.n / 32 + 8) {
+  if (P.trace && TIER == 1 && envWarp && lane == 0 && gw < P.n / 32 + 8) {
     uint32_t* w = P.trace + 4 * (size_t)gw;
     w[0] = (uint32_t)(tw1 - tc0);
     w[1] = (uint32_t)(tw2 - tc1);
@@ -468,7 +556,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   }
   if (P.trace && TIER == 1 && valid) {
     uint32_t* rec = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)i;
-    rec[0] = (e.nVelIters & 0xFFFu) | ((e.nToiEvents & 0xFu) << 12) | ((uint32_t)(e.bailKind & 0xF) << 16) | ((e.dbgShape & 0xFFu) << 20) |
+    rec[0] = (e.nVelIters & 0xFFFu) | ((e.nToiEvents & 0xFu) << 12) | ((uint32_t)(cls & 0xF) << 16) | ((e.dbgShape & 0xFFu) << 20) |
              (e.aborted ? 0x80000000u : 0u);
     rec[1] = (uint32_t)gw;
   }
@@ -499,6 +587,23 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   if (threadIdx.x == 0) {
     if (__any_sync(1u, valid) || true) {
       long long tc4 = clock64();
+      if (P.trace && TIER == 1 && blockIdx.x < P.n / 32 + 8) {
+        uint32_t* w = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)P.n + 12 * (size_t)blockIdx.x;
+        w[0] = (uint32_t)(tc1 - tc0);       // policy + Collide
+        w[1] = (uint32_t)(stampB - tc1);    // solveIslandsBegin
+        w[2] = (uint32_t)(stampV - stampB); // pooled velocity iterations
+        w[3] = (uint32_t)(tc2 - stampV);    // solveIslandsEnd
+        w[4] = (uint32_t)(stampT - tc2);    // TOI collect + first-pass evaluations
+        w[5] = (uint32_t)(tc3 - stampT);    // TOI events
+        w[6] = (uint32_t)(tc4 - tc3);       // finish
+        unsigned sm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        w[7] = sm;
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        w[8] = (uint32_t)gt;                // end time (ns, low word)
+        w[9] = (uint32_t)(tc4 - tc0);
+      }
       unsigned long long* pc = P.phaseClk + 4 * (TIER - 1);
       atomicAdd(&pc[0], (unsigned long long)(tc1 - tc0));
       atomicAdd(&pc[1], (unsigned long long)(tc2 - tc1));
@@ -638,34 +743,49 @@ struct hk_env {
     return P;
   }
   unsigned grid() const { return (unsigned)((n + kBlock - 1) / kBlock); }
-  // general tiers with 2^lanesLog2 envs per warp; tier 1: every work class starts on a warp boundary -> up to 4
-  // partly filled extra warps
-  unsigned gridSlow(int lanesLog2, int block) const {
+  // general tiers with 2^lanesLog2 envs per warp and envWarps env-carrying warps per block; tier 1: every work class
+  // starts on a warp boundary -> up to 4 partly filled extra warps
+  unsigned gridSlow(int lanesPacked, int envWarps) const {
+    int lanesLog2 = 5;
+    for (int c = 0; c < Q_CLASSES; ++c) lanesLog2 = std::min(lanesLog2, (lanesPacked >> (3 * c)) & 7);
     int64_t warps = ((n + (1 << lanesLog2) - 1) >> lanesLog2) + 4;
-    return (unsigned)((warps * 32 + block - 1) / block);
+    return (unsigned)((warps + envWarps - 1) / envWarps);
   }
-  // threads per block of the general tiers: as large as possible (the warps of a block walk the tick phases
-  // together and share fetched code) while still giving every SM about two blocks of the expected queue
-  int blockFor(double expectedFraction) const {
-    int64_t lanes = (int64_t)(expectedFraction * (double)n);
-    int64_t b = (lanes / (2 * 148) + 31) / 32 * 32;
+  // Block shape of tier 1 (measured, profiles/README.md).  The warps of a block walk the tick phases together (shared
+  // instruction fetch, pooled solver / TOI tasks), but a block also waits for its slowest warp in every phase.  Small
+  // batches get ~one block per SM: few env warps plus helper warps for the pooled phases; batches that fill the GPU
+  // get the largest block, all of it env warps.
+  int envWarps1, block1;  // HK_ENV_WARPS / HK_SLOW_BLOCK override
+  void shapeTier1() {
+    const int maxWarps = kSlowBlock / 32;
+    envWarps1 = tiers == 3 ? 6 : (n < 100000 ? 5 : maxWarps);
+    block1 = envWarps1 * 32;  // measured: helper warps do not pay (profiles/README.md)
+    if (const char* e = getenv("HK_ENV_WARPS")) envWarps1 = atoi(e);
+    if (const char* e = getenv("HK_SLOW_BLOCK")) block1 = atoi(e) / 32 * 32;
+    if (envWarps1 < 1) envWarps1 = 1;
+    if (envWarps1 > maxWarps) envWarps1 = maxWarps;
+    if (block1 < envWarps1 * 32) block1 = envWarps1 * 32;
+    if (block1 > kSlowBlock) block1 = kSlowBlock;
+  }
+  int blockTier2() const {
+    int64_t b = ((int64_t)(0.06 * (double)n) / (2 * 148) + 31) / 32 * 32;
     if (b < 64) b = 64;
     if (b > kSlowBlock) b = kSlowBlock;
-    if (const char* e = getenv("HK_SLOW_BLOCK")) b = atoi(e);
     return (int)b;
   }
-  int lanes1, lanes2;  // log2 envs per warp in tier 1 / tier 2 (HK_LANES1 / HK_LANES2 override)
+  int lanes1, lanes2;  // log2 envs per warp in tier 1 / tier 2, 3 bits per work class (HK_LANES1 / HK_LANES2 / HK_CLASS_LANES override)
   bool touch;          // HK_TOUCH=0 disables the touch tier (A/B measurements)
   int phaseSync;       // HK_PHASE_SYNC: which phase barriers the general tiers keep (bit mask, see k_general)
   int launches;        // kernels per tick of the cascade
   // one tick: k_fast over all envs, k_touch over work class 0, the general tier(s) over the rest
   void launchCascade(const StepIO& io, cudaStream_t stream) const {
-    if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (4 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
+    if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (16 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
     k_fast<<<grid(), kBlock, 0, stream>>>(params(), io);
     if (touch) k_touch<<<grid(), kBlock, 0, stream>>>(params(), io);
-    const int b1 = blockFor(touch ? 0.15 : 0.75), b2 = blockFor(0.06);
-    k_general<1><<<gridSlow(lanes1, b1), b1, 0, stream>>>(params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync);
-    if (tiers == 3) k_general<2><<<gridSlow(lanes2, b2), b2, 0, stream>>>(params(), io, 1, lanes2, 0, phaseSync);
+    const int b2 = blockTier2(), w2 = b2 / 32;
+    k_general<1><<<gridSlow(lanes1, envWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0,
+                                                                                     phaseSync, envWarps1);
+    if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), io, 1, lanes2, 0, phaseSync, w2);
   }
 };
 
@@ -707,9 +827,11 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   {
     const char* m = getenv("HK_MONO");
     h->mono = m && m[0] == '1';
+    // measured (profiles/README.md, r1c sweeps): with pooled solves and the block-wide TOI pass the separate budgeted
+    // tier no longer pays at any batch size (262,144 envs: 1.65 ms/tick with 2 tiers, 2.22 with 3); it stays available
+    // through HK_TIERS=3.  Batches that fill the GPU several times over get the touch tier for the puck-racket ticks.
     const char* t = getenv("HK_TIERS");
-    // measured (profiles/README.md): the separate unlimited tier pays off once the batch fills the GPU
-    h->tiers = n_envs >= 200000 ? 3 : 2;
+    h->tiers = 2;
     if (t && (t[0] == '2' || t[0] == '3')) h->tiers = t[0] - '0';
     // envs per warp in the general tiers: dense warps once the batch can fill the GPU, sparse ones below that
     h->lanes1 = 5;  // measured: sparse warps only add instruction-fetch traffic (profiles/README.md)
@@ -718,19 +840,30 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     if (const char* l2 = getenv("HK_LANES2")) h->lanes2 = atoi(l2);
     if (h->lanes1 < 0 || h->lanes1 > 5) h->lanes1 = 5;
     if (h->lanes2 < 0 || h->lanes2 > 5) h->lanes2 = 5;
-    // measured (profiles/README.md): below ~200k envs a tick is bound by its slowest env, and a separate kernel for
-    // the puck-racket ticks only adds a launch in front of that critical path; above, it pays (homogeneous lanes)
+    h->lanes1 *= 01111;  // same value for the four work classes ...
+    h->lanes2 *= 01111;
+    // measured (r1c sweeps): around one general-tier wave per SM (100k..200k envs) half-filled warps for the two
+    // TOI-heavy classes (racket / puck against statics) shorten the critical blocks (+4 %); elsewhere they cost
+    if (n_envs >= 100000 && n_envs < 200000 && !getenv("HK_LANES1")) h->lanes1 = 5 | (5 << 3) | (4 << 6) | (4 << 9);
+    if (const char* cl = getenv("HK_CLASS_LANES")) {  // ... or one digit per class, e.g. "5533"
+      int packed = 0, c = 0;
+      for (; c < Q_CLASSES && cl[c] >= '0' && cl[c] <= '5'; ++c) packed |= (cl[c] - '0') << (3 * c);
+      if (c == Q_CLASSES) h->lanes1 = packed;
+    }
     const char* tt = getenv("HK_TOUCH");
-    h->touch = n_envs >= 200000;
+    h->touch = n_envs >= 500000;
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
-    h->phaseSync = 7;
-    if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 7;
+    h->phaseSync = 15;  // bit 3 (8): pool the single-contact solves too (phase 2)
+    if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 15;
+    h->shapeTier1();
     h->launches = h->mono ? 1 : 2 + (h->touch ? 1 : 0) + (h->tiers == 3 ? 1 : 0);
   }
   Scene S;
   std::memset(&S, 0, sizeof(S));
   scene_build::build(&S);
   cudaError_t err = cudaMemcpyToSymbol(c_scene, &S, sizeof(Scene));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_general<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->cache, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->stats, sizeof(double) * HK_STATS_DIM);
@@ -740,7 +873,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->actBuf, sizeof(float) * 8 * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->phaseClk, sizeof(unsigned long long) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 8);
-  if (err == cudaSuccess && getenv("HK_LANE_TRACE")) err = cudaMalloc(&h->trace, sizeof(uint32_t) * (4 * ((size_t)n_envs / 32 + 8) + 2 * (size_t)n_envs));
+  if (err == cudaSuccess && getenv("HK_LANE_TRACE")) err = cudaMalloc(&h->trace, sizeof(uint32_t) * (16 * ((size_t)n_envs / 32 + 8) + 2 * (size_t)n_envs));
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
   if (err == cudaSuccess) {
@@ -928,7 +1061,7 @@ int hk_debug_phase_cycles(hk_env* h, double* out_host8) {
 int hk_debug_lane_trace(hk_env* h, uint32_t* out_host, int64_t n_words) {
   if (!h || !out_host) return fail(HK_E_INVALID, "hk_debug_lane_trace: NULL argument");
   if (!h->trace) return fail(HK_E_INVALID, "hk_debug_lane_trace: create the env with HK_LANE_TRACE=1");
-  const int64_t have = 4 * (h->n / 32 + 8) + 2 * h->n;
+  const int64_t have = 16 * (h->n / 32 + 8) + 2 * h->n;
   DeviceGuard guard(h->device);
   HK_CUDA(cudaMemcpy(out_host, h->trace, sizeof(uint32_t) * (size_t)(n_words < have ? n_words : have), cudaMemcpyDeviceToHost));
   return HK_OK;

@@ -788,8 +788,7 @@ HK_HD_NOINLINE bool solveVelocityConstraint(Env& e, VC& vc) {
 // Either way the result is numerically identical to running all N sweeps, which is what the oracle does.
 // Specialised sweep loop for the dominant case -- one contact with one manifold point (95 % of solves): every
 // quantity lives in registers, same expression order as solveVelocityConstraint().
-HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
-  const int budget = e.sweepBudget;  // keep the loop free of accesses through e (local memory)
+HK_HD_NOINLINE int runVelocityIterations1Core(VC& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
   int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   const V2 normal = vc.normal;
@@ -798,7 +797,6 @@ HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
   const V2 rA = vc.pt[0].rA, rB = vc.pt[0].rB;
   const float normalMass = vc.pt[0].normalMass, tangentMass = vc.pt[0].tangentMass, bias = vc.pt[0].bias;
   float ni = vc.pt[0].ni, ti = vc.pt[0].ti;
-  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
   V2 vA = A.v, vB = B.v;
   float wA = A.w, wB = B.w;
   // states after the previous sweep (1) and the one before (2)
@@ -863,6 +861,13 @@ HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
   vc.pt[0].ni = ni;
   vc.pt[0].ti = ti;
   A.v = vA; A.w = wA; B.v = vB; B.w = wB;
+  *sweepsOut = sweeps;
+  return result;
+}
+HK_HD int runVelocityIterations1(Env& e, VC& vc, int velIters) {
+  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
+  int sweeps = 0;
+  const int result = runVelocityIterations1Core(vc, A, B, e.sweepBudget, velIters, &sweeps);
   storeVel(e, vc.bA, A);
   storeVel(e, vc.bB, B);
   e.nVelIters += (uint32_t)sweeps;
@@ -871,8 +876,7 @@ HK_HD_NOINLINE int runVelocityIterations1(Env& e, VC& vc, int velIters) {
 
 // Same for one contact with a two-point manifold (racket resting on a wall / goal): tangent rows, then the 2x2
 // block solver of b2ContactSolver::SolveVelocityConstraints, all in registers.
-HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
-  const int budget = e.sweepBudget;  // keep the loop free of accesses through e (local memory)
+HK_HD_NOINLINE int runVelocityIterations2Core(VC& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
   int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   const V2 normal = vc.normal;
@@ -884,7 +888,6 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
   const float bias0 = vc.pt[0].bias, bias1 = vc.pt[1].bias;
   const float k11 = vc.k11, k12 = vc.k12, k22 = vc.k22, n11 = vc.n11, n12 = vc.n12, n21 = vc.n21, n22 = vc.n22;
   float ni0 = vc.pt[0].ni, ti0 = vc.pt[0].ti, ni1 = vc.pt[1].ni, ti1 = vc.pt[1].ti;
-  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
   V2 vA = A.v, vB = B.v;
   float wA = A.w, wB = B.w;
   // previous (p) and before-previous (q) states
@@ -992,6 +995,13 @@ HK_HD_NOINLINE int runVelocityIterations2(Env& e, VC& vc, int velIters) {
   vc.pt[1].ni = ni1;
   vc.pt[1].ti = ti1;
   A.v = vA; A.w = wA; B.v = vB; B.w = wB;
+  *sweepsOut = sweeps;
+  return result;
+}
+HK_HD int runVelocityIterations2(Env& e, VC& vc, int velIters) {
+  Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
+  int sweeps = 0;
+  const int result = runVelocityIterations2Core(vc, A, B, e.sweepBudget, velIters, &sweeps);
   storeVel(e, vc.bA, A);
   storeVel(e, vc.bB, B);
   e.nVelIters += (uint32_t)sweeps;
@@ -1271,8 +1281,7 @@ HK_HD_NOINLINE int runVelocityIterationsFixedCore(VC* vcs, VelTriple& vio, int b
   return result;
 }
 // shape of a multi-contact solve that has a fixed-shape loop: 1..4 = two contacts with (1,1) (1,2) (2,1) (2,2)
-// manifold points, 5 = three single-point contacts, 0 = none (one contact, or anything larger: general loop)
-enum { HK_SOLVE_KINDS = 5 };
+// manifold points, 5 = three single-point contacts, 0 = none (anything larger: general loop; one contact: own loops)
 HK_HD int solveKind(const VC* vcs, int nvc) {
   if (nvc == 2) return 1 + (vcs[0].count - 1) * 2 + (vcs[1].count - 1);
   if (nvc == 3 && vcs[0].count == 1 && vcs[1].count == 1 && vcs[2].count == 1) return 5;

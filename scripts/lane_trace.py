@@ -17,10 +17,11 @@ names = ("policy+collide", "solve", "toi-tasks", "toi-events")
 for rep in range(4):
     env.step()
     torch.cuda.synchronize()
-    buf = np.zeros(4 * nw + 2 * n, np.uint32)
+    buf = np.zeros(16 * nw + 2 * n, np.uint32)
     hk._lib.check(env.L.hk_debug_lane_trace(env._h, buf.ctypes.data, buf.size))
     w = buf[:4 * nw].reshape(nw, 4).astype(np.int64)
-    rec = buf[4 * nw:].reshape(n, 2)
+    rec = buf[4 * nw:4 * nw + 2 * n].reshape(n, 2)
+    blk = buf[4 * nw + 2 * n:].reshape(nw, 12).astype(np.int64)
     used = rec[:, 0] != 0
     r0 = rec[used, 0]
     gw = rec[used, 1]
@@ -37,3 +38,20 @@ for rep in range(4):
             m = gw == t
             print(f"    slow {names[k]} warp {t}: {w[t].tolist()} lanes {m.sum()} sweeps {sorted(sweeps[m].tolist())[-4:]} toi {sorted(toi[m].tolist())[-4:]} "
                   f"shapes(nvc|pts<<4) {sorted(set(shape[m].tolist()))} kinds {sorted(set(kind[m].tolist()))}")
+    cn = ("puck-racket", "racket-static", "puck-static/sensor", "other")
+    for c in range(4):
+        m = kind == c
+        if not m.any():
+            continue
+        ws = np.unique(gw[m])
+        print(f"  class {c} {cn[c]:18s}: envs {m.sum():6d} warps {len(ws):4d}  warp cycles mean " + " ".join(f"{names[k]} {int(w[ws, k].mean())}" for k in range(4)) +
+              f"  total mean {int(tot[ws].mean())} max {int(tot[ws].max())}  events/env {toi[m].mean():.2f} sweeps/env {sweeps[m].mean():.1f}")
+    # block-level critical path: thread 0's stamps at the phase barriers
+    bn = ("collide", "isl-begin", "vel-pool", "isl-end", "toi-eval", "toi-events", "finish")
+    work = blk[:, 9] > 0
+    order = np.argsort(-blk[:, 9])
+    busy = blk[work & (blk[:, 9] > 20000)]
+    print(f"  blocks with work {len(busy)}: total cycles mean {int(busy[:, 9].mean())} max {int(busy[:, 9].max())}; end-time spread {int(busy[:, 8].max() - busy[:, 8].min())} ns")
+    print("  mean share per sub-phase: " + "  ".join(f"{bn[k]} {100 * busy[:, k].sum() / busy[:, 9].sum():.1f}%" for k in range(7)))
+    for b in order[:6]:
+        print(f"    slow block {b} (sm {blk[b, 7]}): total {blk[b, 9]}  " + "  ".join(f"{bn[k]} {blk[b, k]}" for k in range(7)))

@@ -46,6 +46,14 @@ for rep in range(4):
         ws = np.unique(gw[m])
         print(f"  class {c} {cn[c]:18s}: envs {m.sum():6d} warps {len(ws):4d}  warp cycles mean " + " ".join(f"{names[k]} {int(w[ws, k].mean())}" for k in range(4)) +
               f"  total mean {int(tot[ws].mean())} max {int(tot[ws].max())}  events/env {toi[m].mean():.2f} sweeps/env {sweeps[m].mean():.1f}")
+    hist = {}
+    for sh, sw in zip(shape.tolist(), sweeps.tolist()):
+        h = hist.setdefault(sh, [0, 0, 0])
+        h[0] += 1
+        h[1] += sw
+        h[2] += sw >= 180
+    print("  solve shapes (contacts|points<<4: envs, mean sweeps, envs with >=180 sweeps): " +
+          "  ".join(f"{k & 15}c{k >> 4}p: {v[0]}, {v[1] / v[0]:.1f}, {v[2]}" for k, v in sorted(hist.items(), key=lambda kv: -kv[1][0])))
     # block-level critical path: thread 0's stamps at the phase barriers
     bn = ("collide", "isl-begin", "vel-pool", "isl-end", "toi-eval", "toi-events", "finish")
     work = blk[:, 9] > 0

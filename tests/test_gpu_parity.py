@@ -201,9 +201,14 @@ def test_pipeline_variants_are_identical(oracle):
     from parity_util import state_mismatches
     n = 4096
     envs = []
-    for var in ({"HK_MONO": "1"}, {"HK_TIERS": "2"}, {"HK_TIERS": "3"}):
-        old = {k: os.environ.get(k) for k in ("HK_MONO", "HK_TIERS")}
-        for k in ("HK_MONO", "HK_TIERS"):
+    knobs = ("HK_MONO", "HK_TIERS", "HK_TOUCH", "HK_ENV_WARPS", "HK_SLOW_BLOCK", "HK_CLASS_LANES", "HK_PHASE_SYNC")
+    for var in ({"HK_MONO": "1"}, {"HK_TIERS": "2"}, {"HK_TIERS": "3"},
+                # touch tier; 3 env warps + 9 helper warps per block; half-filled warps for two work classes
+                {"HK_TIERS": "2", "HK_TOUCH": "1", "HK_ENV_WARPS": "3", "HK_SLOW_BLOCK": "384", "HK_CLASS_LANES": "5443"},
+                # no pooling of single-contact solves, no phase barriers
+                {"HK_TIERS": "3", "HK_PHASE_SYNC": "0", "HK_ENV_WARPS": "12"}):
+        old = {k: os.environ.get(k) for k in knobs}
+        for k in knobs:
             os.environ.pop(k, None)
         os.environ.update(var)
         try:
@@ -220,8 +225,8 @@ def test_pipeline_variants_are_identical(oracle):
     for e in envs[1:]:
         assert len(state_mismatches(ref, _state(e))) == 0
     s = [e.stats() for e in envs]
-    assert s[0]["episodes"] == s[1]["episodes"] == s[2]["episodes"] > 0
-    assert s[0]["toi_events"] == s[1]["toi_events"] == s[2]["toi_events"]
+    assert s[0]["episodes"] > 0
+    assert all(x["episodes"] == s[0]["episodes"] and x["toi_events"] == s[0]["toi_events"] for x in s[1:])
 
 
 def test_shard_invariance_gpu(oracle):

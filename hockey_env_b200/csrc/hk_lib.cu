@@ -287,7 +287,7 @@ __host__ __device__ constexpr size_t rawBytes(int envLanes) {  // dynamic shared
   return solve > toi ? solve : toi;
 }
 template <int TIER>
-__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync, int envWarps) {
+__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps) {
   __shared__ Scene S;
   extern __shared__ __align__(16) unsigned char sRaw[];  // phase 2: solve tasks; phase 3: TOI tasks + results (rawBytes())
   stageScene(&S);
@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   // (velocity solves, TOI evaluations).  A small batch leaves most of an SM's issue slots idle: helpers let its
   // pooled work spread over more warps than it has env warps.
   const int wib = threadIdx.x >> 5;
-  const bool envWarp = wib < envWarps;
-  const int64_t gw = (int64_t)blockIdx.x * envWarps + wib;  // global env-warp index (env warps only)
+  bool envWarp = wib < envWarps;
+  int64_t gw = (int64_t)blockIdx.x * envWarps + wib;  // global env-warp index (env warps only)
   const int envLanes = envWarps << 5;
   // Only the first `lanes` lanes of a warp carry an env.  With small batches the general tiers are bound by
   // per-warp latency (instruction fetch, local memory), not by issue slots: fewer envs per warp means fewer
@@ -306,7 +306,57 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   int cls = 0;
   bool valid = false;
   int64_t i = 0;
-  if (TIER == 1) {
+  if (TIER == 1 && classWarps) {
+    // Class-homogeneous blocks.  A block waits for its slowest warp in every phase and the ticks of classes 1-3 (TOI
+    // events) are about twice as long as those of class 0 (puck x racket), so a class-0 block carries twice the env
+    // warps of the others.  classWarps > 0: env warps per block and class, 4 bits each (HK_CLASS_WARPS).
+    // classWarps < 0: automatic -- the smallest b (class 0: 2b warps, others: b) for which the tick fits into
+    // -classWarps blocks, i.e. one block per SM in a single wave; batches beyond that use full blocks.
+    unsigned cnt[Q_CLASSES];
+    int64_t nw[Q_CLASSES];
+#pragma unroll
+    for (int c = 0; c < Q_CLASSES; ++c) {
+      cnt[c] = c < firstClass ? 0u : *((volatile uint32_t*)&P.qctl[c]);
+      const int ll = (lanesLog2 >> (3 * c)) & 7;
+      nw[c] = ((int64_t)cnt[c] + (1 << ll) - 1) >> ll;
+    }
+    int packed = classWarps;
+    if (classWarps < 0) {
+      const int maxW = envWarps, target = -classWarps;
+      int b = 1;
+      for (; b < maxW; ++b) {
+        const int w0_ = min(2 * b, maxW);
+        int64_t blocks = (nw[0] + w0_ - 1) / w0_;
+#pragma unroll
+        for (int c = 1; c < Q_CLASSES; ++c) blocks += (nw[c] + b - 1) / b;
+        if (blocks <= target) break;
+      }
+      packed = min(2 * b, maxW) | (b << 4) | (b << 8) | (b << 12);
+    }
+    int64_t w0 = 0, b0 = 0;
+    envWarp = false;
+#pragma unroll
+    for (int c = 0; c < Q_CLASSES; ++c) {
+      const int ll = (lanesLog2 >> (3 * c)) & 7, lanes = 1 << ll;
+      const int wpb = (packed >> (4 * c)) & 15;
+      const int64_t nb = (nw[c] + wpb - 1) / wpb;
+      if (!valid && (int64_t)blockIdx.x >= b0 && (int64_t)blockIdx.x < b0 + nb && wib < wpb) {
+        const int64_t w = ((int64_t)blockIdx.x - b0) * wpb + wib;
+        if (w < nw[c]) {
+          envWarp = true;
+          gw = w0 + w;
+          const int64_t j = (w << ll) + lane;
+          if (lane < lanes && j < (int64_t)cnt[c]) {
+            valid = true;
+            cls = c;
+            i = P.queue[(int64_t)c * P.n + j];
+          }
+        }
+      }
+      w0 += nw[c];
+      b0 += nb;
+    }
+  } else if (TIER == 1) {
     int64_t w0 = 0;
 #pragma unroll
     for (int c = 0; c < Q_CLASSES; ++c) {
@@ -745,17 +795,25 @@ struct hk_env {
   unsigned grid() const { return (unsigned)((n + kBlock - 1) / kBlock); }
   // general tiers with 2^lanesLog2 envs per warp and envWarps env-carrying warps per block; tier 1: every work class
   // starts on a warp boundary -> up to 4 partly filled extra warps
-  unsigned gridSlow(int lanesPacked, int envWarps) const {
+  unsigned gridSlow(int lanesPacked, int envWarps, int classWarpsPacked = 0) const {
     int lanesLog2 = 5;
     for (int c = 0; c < Q_CLASSES; ++c) lanesLog2 = std::min(lanesLog2, (lanesPacked >> (3 * c)) & 7);
     int64_t warps = ((n + (1 << lanesLog2) - 1) >> lanesLog2) + 4;
-    return (unsigned)((warps + envWarps - 1) / envWarps);
+    if (classWarpsPacked < 0)  // automatic shape: at most -classWarpsPacked blocks unless even full blocks do not fit
+      return (unsigned)std::max<int64_t>(-classWarpsPacked, (warps + envWarps - 1) / envWarps + Q_CLASSES);
+    if (classWarpsPacked > 0) {
+      envWarps = 15;
+      for (int c = 0; c < Q_CLASSES; ++c) envWarps = std::min(envWarps, (classWarpsPacked >> (4 * c)) & 15);
+    }
+    return (unsigned)((warps + envWarps - 1) / envWarps) + (classWarpsPacked ? Q_CLASSES : 0);
   }
   // Block shape of tier 1 (measured, profiles/README.md).  The warps of a block walk the tick phases together (shared
   // instruction fetch, pooled solver / TOI tasks), but a block also waits for its slowest warp in every phase.  Small
   // batches get ~one block per SM: few env warps plus helper warps for the pooled phases; batches that fill the GPU
   // get the largest block, all of it env warps.
   int envWarps1, block1;  // HK_ENV_WARPS / HK_SLOW_BLOCK override
+  int classWarps1 = 0;    // HK_CLASS_WARPS: env warps per block and work class, 4 bits each (0: blocks cut from the sorted queue; < 0: automatic)
+  int targetBlocks = 140; // HK_TARGET_BLOCKS: blocks the automatic shape aims at (one wave, one block per SM)
   void shapeTier1() {
     const int maxWarps = kSlowBlock / 32;
     envWarps1 = tiers == 3 ? 6 : (n < 100000 ? 5 : maxWarps);
@@ -766,6 +824,32 @@ struct hk_env {
     if (envWarps1 > maxWarps) envWarps1 = maxWarps;
     if (block1 < envWarps1 * 32) block1 = envWarps1 * 32;
     if (block1 > kSlowBlock) block1 = kSlowBlock;
+    if (const char* e = getenv("HK_TARGET_BLOCKS")) targetBlocks = atoi(e);
+    // automatic class-homogeneous block shape (k_general) with up to envWarps1 env warps per block
+    if (tiers == 2 && !getenv("HK_ENV_WARPS") && targetBlocks > 0) {
+      envWarps1 = n <= 40000 ? 4 : (n <= 100000 ? 8 : maxWarps);
+      block1 = envWarps1 * 32;
+      if (const char* e = getenv("HK_SLOW_BLOCK")) block1 = std::min(kSlowBlock, std::max(block1, atoi(e) / 32 * 32));
+      classWarps1 = -targetBlocks;
+    }
+    if (const char* cw = getenv("HK_CLASS_WARPS")) {  // one hex digit (1..c) per class, e.g. "8444"; "0": sorted-queue cut
+      int packed = 0, c = 0, mx = 0;
+      for (; c < Q_CLASSES; ++c) {
+        const int v = cw[c] >= '1' && cw[c] <= '9' ? cw[c] - '0' : (cw[c] >= 'a' && cw[c] <= 'c' ? cw[c] - 'a' + 10 : 0);
+        if (!v) break;
+        packed |= v << (4 * c);
+        mx = std::max(mx, v);
+      }
+      if (c == Q_CLASSES) {
+        classWarps1 = packed;
+        envWarps1 = mx;
+        block1 = std::max(mx * 32, getenv("HK_SLOW_BLOCK") ? std::min(kSlowBlock, atoi(getenv("HK_SLOW_BLOCK")) / 32 * 32) : 0);
+      } else if (cw[0] == '0') {
+        classWarps1 = 0;
+        envWarps1 = n < 100000 ? 5 : maxWarps;
+        block1 = envWarps1 * 32;
+      }
+    }
   }
   int blockTier2() const {
     int64_t b = ((int64_t)(0.06 * (double)n) / (2 * 148) + 31) / 32 * 32;
@@ -783,9 +867,9 @@ struct hk_env {
     k_fast<<<grid(), kBlock, 0, stream>>>(params(), io);
     if (touch) k_touch<<<grid(), kBlock, 0, stream>>>(params(), io);
     const int b2 = blockTier2(), w2 = b2 / 32;
-    k_general<1><<<gridSlow(lanes1, envWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0,
-                                                                                     phaseSync, envWarps1);
-    if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), io, 1, lanes2, 0, phaseSync, w2);
+    k_general<1><<<gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(
+        params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
+    if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), io, 1, lanes2, 0, phaseSync, w2, 0);
   }
 };
 
@@ -855,6 +939,9 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
     h->phaseSync = 15;  // bit 3 (8): pool the single-contact solves too (phase 2)
     if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 15;
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 16) sms = 148;
+    h->targetBlocks = sms;  // one general-tier block per SM in a single wave (measured: 148 > 140 > 132 on a 148-SM B200)
     h->shapeTier1();
     h->launches = h->mono ? 1 : 2 + (h->touch ? 1 : 0) + (h->tiers == 3 ? 1 : 0);
   }

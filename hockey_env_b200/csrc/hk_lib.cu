@@ -267,7 +267,7 @@ constexpr int kMidSweeps = 24;
 // Velocity solves of a block are pooled in shared memory (phase 2 of k_general) and dealt to its warps as units of one
 // loop shape each: a warp never runs two different 180-sweep loops one after the other unless the block holds more
 // units than warps, and the lanes of a unit all execute the same register-resident loop.
-struct SolveTask {   // multi-contact solve with a fixed-shape loop (solveKind 1..5)
+struct SolveTask {   // multi-contact solve with a fixed-shape loop (solveKind 1..8)
   VC vcs[3];
   VelTriple v;
   int result, sweeps;
@@ -277,7 +277,6 @@ struct Solve1Task {  // one contact, one or two manifold points
   Vel A, B;
   int result, sweeps;
 };
-enum { HK_MULTI_KINDS = 5 };
 constexpr int kSolveSlots = 12;     // multi-contact tasks per loop shape and block; the rest is solved in place
 constexpr int kTasksPerLane = 3;    // first-pass TOI evaluations a lane may file (phase 3)
 constexpr size_t kRawMulti = sizeof(SolveTask) * HK_MULTI_KINDS * kSolveSlots;
@@ -423,18 +422,20 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   IslandCtx ctx;
   ctx.nvc = 0;
   long long stampB = 0, stampV = 0, stampT = 0;  // diagnostics: block-level stamps inside phases 2 and 3
+  __shared__ unsigned long long sSlowUnit;       // diagnostics: (cycles << 8 | type) of the slowest pooled solve unit
   if (valid) solveIslandsBegin(S, cache, e, dt, ctx);
   {
     SolveTask* mtasks = reinterpret_cast<SolveTask*>(sRaw);
     Solve1Task* stasks = reinterpret_cast<Solve1Task*>(sRaw + kRawMulti);  // 1-point tasks from the front, 2-point from the back
-    __shared__ int sKindCount[HK_MULTI_KINDS + 2];  // [0..4] multi kinds 1..5, [5] one contact x 1 point, [6] one contact x 2 points
+    __shared__ int sKindCount[HK_MULTI_KINDS + 2];  // multi kinds 1..8, then one contact x 1 point, one contact x 2 points
     if (threadIdx.x < HK_MULTI_KINDS + 2) sKindCount[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sSlowUnit = 0;
     __syncthreads();
     stampB = clock64();
     const int nwarps = blockDim.x >> 5;
     const int budget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
     const bool pool1 = (phaseSync & 8) != 0;  // also pool the single-contact solves
-    int kind = 0, slot = 0;  // kind 1..5: multi; 6: single contact, 1 point; 7: single contact, 2 points
+    int kind = 0, slot = 0;  // kind 1..HK_MULTI_KINDS: multi; then single contact, 1 point; single contact, 2 points
     if (valid && ctx.nvc >= 2) {
       kind = solveKind(ctx.vcs, ctx.nvc);
       if (kind) {
@@ -442,11 +443,11 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         if (slot >= kSolveSlots) kind = 0;  // no room: solved in place
       }
     } else if (valid && ctx.nvc == 1 && pool1) {
-      kind = 5 + ctx.vcs[0].count;
+      kind = HK_MULTI_KINDS + ctx.vcs[0].count;
       slot = atomicAdd(&sKindCount[kind - 1], 1);
     }
-    if (kind >= 6) {
-      Solve1Task& t = stasks[kind == 6 ? slot : envLanes - 1 - slot];
+    if (kind > HK_MULTI_KINDS) {
+      Solve1Task& t = stasks[kind == HK_MULTI_KINDS + 1 ? slot : envLanes - 1 - slot];
       t.vc = ctx.vcs[0];
       t.A = loadVel(e, ctx.vcs[0].bA);
       t.B = loadVel(e, ctx.vcs[0].bB);
@@ -461,11 +462,11 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     {
       // unit list, identical in every warp: the multi-contact shapes that have tasks (heaviest loops first), then the
       // 2-point chunks, then the 1-point chunks; spare warps split the 1-point tasks into smaller chunks
-      const int n1 = sKindCount[5], n2 = sKindCount[6];
+      const int n1 = sKindCount[HK_MULTI_KINDS], n2 = sKindCount[HK_MULTI_KINDS + 1];
       int nm = 0, mk_[HK_MULTI_KINDS];
 #pragma unroll
       for (int q = 0; q < HK_MULTI_KINDS; ++q) {
-        const int k = q == 0 ? 4 : (q == 1 ? 2 : (q == 2 ? 3 : (q == 3 ? 5 : 1)));
+        const int k = q == 0 ? 4 : (q == 1 ? 6 : (q == 2 ? 7 : (q == 3 ? 8 : (q == 4 ? 2 : (q == 5 ? 3 : (q == 6 ? 5 : 1))))));
         if (sKindCount[k - 1] > 0) mk_[nm++] = k;
       }
       const int c2 = (n2 + 31) >> 5;
@@ -473,8 +474,12 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
       const int spare = nwarps - nm - c2;
       if (spare > c1) c1 = min(spare, (n1 + 3) >> 2);
       const int units = nm + c2 + c1;
-      for (int u = wib; u < units; u += nwarps) {
+      // first round: unit w -> warp w; further rounds run backwards (the first warps hold the heavy multi-contact loops)
+      for (int r = 0, u = wib; u < units; ++r, u = r * nwarps + ((r & 1) ? nwarps - 1 - wib : wib)) {
+        const long long tu0 = P.trace ? clock64() : 0;
+        int utype = 10;  // diagnostics: 1..8 multi-contact shape, 9 two-point chunk, 10 one-point chunk, 11 in place
         if (u < nm) {
+          utype = mk_[u];
           const int k = mk_[u];
           if (lane < min(sKindCount[k - 1], kSolveSlots)) {
             SolveTask& t = mtasks[(k - 1) * kSolveSlots + lane];
@@ -509,17 +514,24 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
             t.sweeps = sweeps;
           }
         }
+        if (u >= nm && u < nm + c2) utype = 9;
+        if (P.trace && lane == 0) atomicMax(&sSlowUnit, ((unsigned long long)(clock64() - tu0) << 8) | (unsigned)utype);
       }
     }
     int itc = 0;
-    if (valid && ctx.nvc > 0 && !kind) itc = runVelocityIterations(e, ctx.vcs, ctx.nvc, 6 * 30);
+    {
+      const long long tu0 = P.trace ? clock64() : 0;
+      const bool inPlace = valid && ctx.nvc > 0 && !kind;
+      if (inPlace) itc = runVelocityIterations(e, ctx.vcs, ctx.nvc, 6 * 30);
+      if (P.trace && __any_sync(0xffffffffu, inPlace) && lane == 0) atomicMax(&sSlowUnit, ((unsigned long long)(clock64() - tu0) << 8) | 11u);
+    }
     __syncthreads();
     stampV = clock64();
-    if (kind >= 6) {
-      const Solve1Task& t = stasks[kind == 6 ? slot : envLanes - 1 - slot];
+    if (kind > HK_MULTI_KINDS) {
+      const Solve1Task& t = stasks[kind == HK_MULTI_KINDS + 1 ? slot : envLanes - 1 - slot];
       ctx.vcs[0].pt[0].ni = t.vc.pt[0].ni;
       ctx.vcs[0].pt[0].ti = t.vc.pt[0].ti;
-      if (kind == 7) {
+      if (kind == HK_MULTI_KINDS + 2) {
         ctx.vcs[0].pt[1].ni = t.vc.pt[1].ni;
         ctx.vcs[0].pt[1].ti = t.vc.pt[1].ti;
       }
@@ -653,6 +665,8 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
         w[8] = (uint32_t)gt;                // end time (ns, low word)
         w[9] = (uint32_t)(tc4 - tc0);
+        w[10] = (uint32_t)(sSlowUnit >> 8);
+        w[11] = (uint32_t)(sSlowUnit & 0xFF);
       }
       unsigned long long* pc = P.phaseClk + 4 * (TIER - 1);
       atomicAdd(&pc[0], (unsigned long long)(tc1 - tc0));

@@ -1281,10 +1281,16 @@ HK_HD_NOINLINE int runVelocityIterationsFixedCore(VC* vcs, VelTriple& vio, int b
   return result;
 }
 // shape of a multi-contact solve that has a fixed-shape loop: 1..4 = two contacts with (1,1) (1,2) (2,1) (2,2)
-// manifold points, 5 = three single-point contacts, 0 = none (anything larger: general loop; one contact: own loops)
+// manifold points, 5 = three single-point contacts, 6..8 = three contacts with (1,1,2) (1,2,1) (2,1,1) points, 0 = none
+// (anything larger: general loop, ~3,500 cycles per sweep against ~1,400 here; one contact: own loops)
+enum { HK_MULTI_KINDS = 8 };
 HK_HD int solveKind(const VC* vcs, int nvc) {
   if (nvc == 2) return 1 + (vcs[0].count - 1) * 2 + (vcs[1].count - 1);
-  if (nvc == 3 && vcs[0].count == 1 && vcs[1].count == 1 && vcs[2].count == 1) return 5;
+  if (nvc == 3) {
+    const int c0 = vcs[0].count, c1 = vcs[1].count, c2 = vcs[2].count;
+    if (c0 + c1 + c2 == 3) return 5;
+    if (c0 + c1 + c2 == 4) return c2 == 2 ? 6 : (c1 == 2 ? 7 : 8);
+  }
   return 0;
 }
 HK_HD int runVelocityIterationsKind(int kind, VC* vcs, VelTriple& v, int budget, int velIters, int* sweepsOut) {
@@ -1293,7 +1299,10 @@ HK_HD int runVelocityIterationsKind(int kind, VC* vcs, VelTriple& v, int budget,
     case 2: return runVelocityIterationsFixedCore<1, 2, 0>(vcs, v, budget, velIters, sweepsOut);
     case 3: return runVelocityIterationsFixedCore<2, 1, 0>(vcs, v, budget, velIters, sweepsOut);
     case 4: return runVelocityIterationsFixedCore<2, 2, 0>(vcs, v, budget, velIters, sweepsOut);
-    default: return runVelocityIterationsFixedCore<1, 1, 1>(vcs, v, budget, velIters, sweepsOut);
+    case 5: return runVelocityIterationsFixedCore<1, 1, 1>(vcs, v, budget, velIters, sweepsOut);
+    case 6: return runVelocityIterationsFixedCore<1, 1, 2>(vcs, v, budget, velIters, sweepsOut);
+    case 7: return runVelocityIterationsFixedCore<1, 2, 1>(vcs, v, budget, velIters, sweepsOut);
+    default: return runVelocityIterationsFixedCore<2, 1, 1>(vcs, v, budget, velIters, sweepsOut);
   }
 }
 

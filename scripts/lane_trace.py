@@ -62,4 +62,9 @@ for rep in range(4):
     print(f"  blocks with work {len(busy)}: total cycles mean {int(busy[:, 9].mean())} max {int(busy[:, 9].max())}; end-time spread {int(busy[:, 8].max() - busy[:, 8].min())} ns")
     print("  mean share per sub-phase: " + "  ".join(f"{bn[k]} {100 * busy[:, k].sum() / busy[:, 9].sum():.1f}%" for k in range(7)))
     for b in order[:6]:
-        print(f"    slow block {b} (sm {blk[b, 7]}): total {blk[b, 9]}  " + "  ".join(f"{bn[k]} {blk[b, k]}" for k in range(7)))
+        print(f"    slow block {b} (sm {blk[b, 7]}): total {blk[b, 9]}  " + "  ".join(f"{bn[k]} {blk[b, k]}" for k in range(7)) + f"  slowest solve unit: type {blk[b, 11]} {blk[b, 10]} cycles")
+    ut = ("-", "2c(1,1)", "2c(1,2)", "2c(2,1)", "2c(2,2)", "3c(1,1,1)", "3c(1,1,2)", "3c(1,2,1)", "3c(2,1,1)", "1c2p chunk", "1c1p chunk", "in place")
+    for k in range(1, 12):
+        m = busy[:, 11] == k
+        if m.any():
+            print(f"    slowest unit is {ut[k]:10s} in {m.sum():3d} blocks: cycles mean {int(busy[m, 10].mean())} max {int(busy[m, 10].max())}")

@@ -270,18 +270,27 @@ constexpr int kMidSweeps = 24;
 struct SolveTask {   // multi-contact solve with a fixed-shape loop (solveKind 1..8)
   VC vcs[3];
   VelTriple v;
-  int result, sweeps;
+  int result, sweeps, kind;
 };
-struct Solve1Task {  // one contact, one or two manifold points
+struct Solve2Task {  // one contact, two manifold points
   VC vc;
   Vel A, B;
   int result, sweeps;
 };
-constexpr int kSolveSlots = 12;     // multi-contact tasks per loop shape and block; the rest is solved in place
+struct Solve1Task {  // one contact, one manifold point (95 % of the solves)
+  VC1 vc;
+  Vel A, B;
+  int result, sweeps;
+};
+// Shared memory is taken out of L1, and the general path keeps its per-thread state (several KB) in local memory, i.e.
+// in L1 (measured: profiles/README.md, carve-out sweep), so the pools are compact: one slot array for all multi-contact
+// shapes (tagged with their kind), a small one for the two-point solves, 96 B per env lane for the one-point solves.
+constexpr int kMultiSlots = 24;     // multi-contact tasks per block (<= 32: a warp finds its shape's tasks with one ballot); the rest is solved in place
 constexpr int kTasksPerLane = 3;    // first-pass TOI evaluations a lane may file (phase 3)
-constexpr size_t kRawMulti = sizeof(SolveTask) * HK_MULTI_KINDS * kSolveSlots;
+constexpr size_t kRawMulti = sizeof(SolveTask) * kMultiSlots;
+__host__ __device__ constexpr int twoPointSlots(int envLanes) { return envLanes / 8 < 16 ? 16 : envLanes / 8; }
 __host__ __device__ constexpr size_t rawBytes(int envLanes) {  // dynamic shared memory of k_general for envLanes env lanes
-  const size_t solve = kRawMulti + sizeof(Solve1Task) * (size_t)envLanes;
+  const size_t solve = kRawMulti + sizeof(Solve2Task) * (size_t)twoPointSlots(envLanes) + sizeof(Solve1Task) * (size_t)envLanes;
   const size_t toi = (sizeof(ToiTask) + sizeof(float)) * (size_t)envLanes * kTasksPerLane;
   return solve > toi ? solve : toi;
 }
@@ -426,9 +435,12 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   if (valid) solveIslandsBegin(S, cache, e, dt, ctx);
   {
     SolveTask* mtasks = reinterpret_cast<SolveTask*>(sRaw);
-    Solve1Task* stasks = reinterpret_cast<Solve1Task*>(sRaw + kRawMulti);  // 1-point tasks from the front, 2-point from the back
-    __shared__ int sKindCount[HK_MULTI_KINDS + 2];  // multi kinds 1..8, then one contact x 1 point, one contact x 2 points
-    if (threadIdx.x < HK_MULTI_KINDS + 2) sKindCount[threadIdx.x] = 0;
+    Solve2Task* s2tasks = reinterpret_cast<Solve2Task*>(sRaw + kRawMulti);
+    const int cap2 = twoPointSlots(envLanes);
+    Solve1Task* s1tasks = reinterpret_cast<Solve1Task*>(sRaw + kRawMulti + sizeof(Solve2Task) * (size_t)cap2);
+    // counts: multi kinds 1..8, one contact x 1 point, one contact x 2 points, all multi-contact slots handed out
+    __shared__ int sKindCount[HK_MULTI_KINDS + 3];
+    if (threadIdx.x < HK_MULTI_KINDS + 3) sKindCount[threadIdx.x] = 0;
     if (threadIdx.x == 0) sSlowUnit = 0;
     __syncthreads();
     stampB = clock64();
@@ -439,20 +451,28 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     if (valid && ctx.nvc >= 2) {
       kind = solveKind(ctx.vcs, ctx.nvc);
       if (kind) {
-        slot = atomicAdd(&sKindCount[kind - 1], 1);
-        if (slot >= kSolveSlots) kind = 0;  // no room: solved in place
+        slot = atomicAdd(&sKindCount[HK_MULTI_KINDS + 2], 1);
+        if (slot >= kMultiSlots) kind = 0;  // no room: solved in place
+        else atomicAdd(&sKindCount[kind - 1], 1);
       }
     } else if (valid && ctx.nvc == 1 && pool1) {
       kind = HK_MULTI_KINDS + ctx.vcs[0].count;
       slot = atomicAdd(&sKindCount[kind - 1], 1);
+      if (kind == HK_MULTI_KINDS + 2 && slot >= cap2) kind = 0;
     }
-    if (kind > HK_MULTI_KINDS) {
-      Solve1Task& t = stasks[kind == HK_MULTI_KINDS + 1 ? slot : envLanes - 1 - slot];
+    if (kind == HK_MULTI_KINDS + 1) {
+      Solve1Task& t = s1tasks[slot];
+      t.vc = vc1Of(ctx.vcs[0]);
+      t.A = loadVel(e, ctx.vcs[0].bA);
+      t.B = loadVel(e, ctx.vcs[0].bB);
+    } else if (kind == HK_MULTI_KINDS + 2) {
+      Solve2Task& t = s2tasks[slot];
       t.vc = ctx.vcs[0];
       t.A = loadVel(e, ctx.vcs[0].bA);
       t.B = loadVel(e, ctx.vcs[0].bB);
     } else if (kind) {
-      SolveTask& t = mtasks[(kind - 1) * kSolveSlots + slot];
+      SolveTask& t = mtasks[slot];
+      t.kind = kind;
       for (int k = 0; k < ctx.nvc; ++k) t.vcs[k] = ctx.vcs[k];
       t.v.b0 = loadVel(e, 0);
       t.v.b1 = loadVel(e, 1);
@@ -462,7 +482,8 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     {
       // unit list, identical in every warp: the multi-contact shapes that have tasks (heaviest loops first), then the
       // 2-point chunks, then the 1-point chunks; spare warps split the 1-point tasks into smaller chunks
-      const int n1 = sKindCount[HK_MULTI_KINDS], n2 = sKindCount[HK_MULTI_KINDS + 1];
+      const int n1 = sKindCount[HK_MULTI_KINDS], n2 = min(sKindCount[HK_MULTI_KINDS + 1], cap2);
+      const int nMulti = min(sKindCount[HK_MULTI_KINDS + 2], kMultiSlots);
       int nm = 0, mk_[HK_MULTI_KINDS];
 #pragma unroll
       for (int q = 0; q < HK_MULTI_KINDS; ++q) {
@@ -481,8 +502,10 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         if (u < nm) {
           utype = mk_[u];
           const int k = mk_[u];
-          if (lane < min(sKindCount[k - 1], kSolveSlots)) {
-            SolveTask& t = mtasks[(k - 1) * kSolveSlots + lane];
+          // this shape's tasks among the block's multi-contact slots: lane l takes the l-th of them
+          const unsigned mine = __ballot_sync(0xffffffffu, lane < nMulti && mtasks[lane < nMulti ? lane : 0].kind == k);
+          if (lane < __popc(mine)) {
+            SolveTask& t = mtasks[__fns(mine, 0, lane + 1)];
             VelTriple v = t.v;
             int sweeps = 0;
             t.result = runVelocityIterationsKind(k, t.vcs, v, budget, 6 * 30, &sweeps);
@@ -492,7 +515,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         } else if (u < nm + c2) {
           const int j = ((u - nm) << 5) + lane;
           if (j < n2) {
-            Solve1Task& t = stasks[envLanes - 1 - j];
+            Solve2Task& t = s2tasks[j];
             Vel A = t.A, B = t.B;
             int sweeps = 0;
             t.result = runVelocityIterations2Core(t.vc, A, B, budget, 6 * 30, &sweeps);
@@ -505,7 +528,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
           const int lo = (int)(((long long)n1 * c) / c1), hi = (int)(((long long)n1 * (c + 1)) / c1);
           const int j = lo + lane;
           if (j < hi) {
-            Solve1Task& t = stasks[j];
+            Solve1Task& t = s1tasks[j];
             Vel A = t.A, B = t.B;
             int sweeps = 0;
             t.result = runVelocityIterations1Core(t.vc, A, B, budget, 6 * 30, &sweeps);
@@ -527,20 +550,26 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     }
     __syncthreads();
     stampV = clock64();
-    if (kind > HK_MULTI_KINDS) {
-      const Solve1Task& t = stasks[kind == HK_MULTI_KINDS + 1 ? slot : envLanes - 1 - slot];
+    if (kind == HK_MULTI_KINDS + 1) {
+      const Solve1Task& t = s1tasks[slot];
+      ctx.vcs[0].pt[0].ni = t.vc.ni;
+      ctx.vcs[0].pt[0].ti = t.vc.ti;
+      storeVel(e, ctx.vcs[0].bA, t.A);
+      storeVel(e, ctx.vcs[0].bB, t.B);
+      e.nVelIters += (uint32_t)t.sweeps;
+      itc = t.result;
+    } else if (kind == HK_MULTI_KINDS + 2) {
+      const Solve2Task& t = s2tasks[slot];
       ctx.vcs[0].pt[0].ni = t.vc.pt[0].ni;
       ctx.vcs[0].pt[0].ti = t.vc.pt[0].ti;
-      if (kind == HK_MULTI_KINDS + 2) {
-        ctx.vcs[0].pt[1].ni = t.vc.pt[1].ni;
-        ctx.vcs[0].pt[1].ti = t.vc.pt[1].ti;
-      }
+      ctx.vcs[0].pt[1].ni = t.vc.pt[1].ni;
+      ctx.vcs[0].pt[1].ti = t.vc.pt[1].ti;
       storeVel(e, ctx.vcs[0].bA, t.A);
       storeVel(e, ctx.vcs[0].bB, t.B);
       e.nVelIters += (uint32_t)t.sweeps;
       itc = t.result;
     } else if (kind) {
-      const SolveTask& t = mtasks[(kind - 1) * kSolveSlots + slot];
+      const SolveTask& t = mtasks[slot];
       for (int k = 0; k < ctx.nvc; ++k) {
         ctx.vcs[k].pt[0].ni = t.vcs[k].pt[0].ni;
         ctx.vcs[k].pt[0].ti = t.vcs[k].pt[0].ti;
@@ -602,7 +631,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   }
   if (phaseSync & 4) __syncthreads();
   long long tc3 = clock64();
-  if (phaseSync & 4) {  // diagnostics: block-wide max of per-lane TOI evaluation / event cycles
+  if (P.trace && (phaseSync & 4)) {  // diagnostics (HK_LANE_TRACE=1): block-wide max of per-lane TOI evaluation / event cycles
     __shared__ unsigned long long sMaxEval, sMaxEvent;
     if (threadIdx.x == 0) { sMaxEval = 0; sMaxEvent = 0; }
     __syncthreads();
@@ -622,11 +651,21 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
              (e.aborted ? 0x80000000u : 0u);
     rec[1] = (uint32_t)gw;
   }
+  __shared__ unsigned sFin[4];  // diagnostics: block max of per-warp cycles in commit / tickFinish / store+flush, done lanes
+  if (P.trace) {
+    if (threadIdx.x < 4) sFin[threadIdx.x] = 0;
+    __syncthreads();
+  }
+  const long long tf0 = clock64();
+  long long tf1 = tf0, tf2 = tf0;
   if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
     if (!e.aborted) {
       worldStepFinish(cache, e);
       envStepAfterWorld(P.cfg, e);
+      tf1 = clock64();
+      if (P.trace && e.done) atomicAdd(&sFin[3], 1u);
       tickFinish(S, P.cfg, e, env_id, (size_t)i, io, io.write != 0, st, had1, had2);
+      tf2 = clock64();
       storeEnv(P.core, P.n, i, e);
     } else {
       need = true;
@@ -644,13 +683,18 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     }
     flushStats(P.stats, st);
   }
+  if (P.trace && valid) {
+    atomicMax(&sFin[0], (unsigned)(tf1 - tf0));
+    atomicMax(&sFin[1], (unsigned)(tf2 - tf1));
+    atomicMax(&sFin[2], (unsigned)(clock64() - tf2));
+  }
   // the last block to finish re-arms this tier's queue(s) for the next tick
   __syncthreads();
   if (threadIdx.x == 0) {
     if (__any_sync(1u, valid) || true) {
       long long tc4 = clock64();
       if (P.trace && TIER == 1 && blockIdx.x < P.n / 32 + 8) {
-        uint32_t* w = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)P.n + 12 * (size_t)blockIdx.x;
+        uint32_t* w = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)P.n + 16 * (size_t)blockIdx.x;
         w[0] = (uint32_t)(tc1 - tc0);       // policy + Collide
         w[1] = (uint32_t)(stampB - tc1);    // solveIslandsBegin
         w[2] = (uint32_t)(stampV - stampB); // pooled velocity iterations
@@ -667,6 +711,10 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         w[9] = (uint32_t)(tc4 - tc0);
         w[10] = (uint32_t)(sSlowUnit >> 8);
         w[11] = (uint32_t)(sSlowUnit & 0xFF);
+        w[12] = sFin[0];
+        w[13] = sFin[1];
+        w[14] = sFin[2];
+        w[15] = sFin[3];
       }
       unsigned long long* pc = P.phaseClk + 4 * (TIER - 1);
       atomicAdd(&pc[0], (unsigned long long)(tc1 - tc0));
@@ -876,8 +924,22 @@ struct hk_env {
   int phaseSync;       // HK_PHASE_SYNC: which phase barriers the general tiers keep (bit mask, see k_general)
   int launches;        // kernels per tick of the cascade
   // one tick: k_fast over all envs, k_touch over work class 0, the general tier(s) over the rest
+  // The kernels keep several KB of per-thread state in local memory, i.e. in L1: ask for the smallest shared-memory
+  // carve-out that holds the blocks an SM will actually run (the driver's default sizes it for the register-limited
+  // block count, which at small blocks leaves almost no L1).  HK_CARVEOUT=0 keeps the driver default.
+  bool carveout = true;
+  void shapeSharedMemory() const {
+    if (!carveout) return;
+    auto pct = [](size_t bytes) { return (int)std::min<size_t>(100, (bytes * 100 + 228 * 1024 - 1) / (228 * 1024)); };
+    const size_t stat = sizeof(Scene) + 256;
+    const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
+    cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? 1 : perSm1)));
+    cudaFuncSetAttribute(k_fast, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 5));
+    cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 3));
+  }
   void launchCascade(const StepIO& io, cudaStream_t stream) const {
-    if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (16 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
+    shapeSharedMemory();
+    if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (20 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
     k_fast<<<grid(), kBlock, 0, stream>>>(params(), io);
     if (touch) k_touch<<<grid(), kBlock, 0, stream>>>(params(), io);
     const int b2 = blockTier2(), w2 = b2 / 32;
@@ -951,6 +1013,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     const char* tt = getenv("HK_TOUCH");
     h->touch = n_envs >= 500000;
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
+    if (const char* co = getenv("HK_CARVEOUT")) h->carveout = co[0] != '0';
     h->phaseSync = 15;  // bit 3 (8): pool the single-contact solves too (phase 2)
     if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 15;
     int sms = 148;
@@ -974,7 +1037,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->actBuf, sizeof(float) * 8 * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->phaseClk, sizeof(unsigned long long) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 8);
-  if (err == cudaSuccess && getenv("HK_LANE_TRACE")) err = cudaMalloc(&h->trace, sizeof(uint32_t) * (16 * ((size_t)n_envs / 32 + 8) + 2 * (size_t)n_envs));
+  if (err == cudaSuccess && getenv("HK_LANE_TRACE")) err = cudaMalloc(&h->trace, sizeof(uint32_t) * (20 * ((size_t)n_envs / 32 + 8) + 2 * (size_t)n_envs));
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
   if (err == cudaSuccess) {
@@ -1162,7 +1225,7 @@ int hk_debug_phase_cycles(hk_env* h, double* out_host8) {
 int hk_debug_lane_trace(hk_env* h, uint32_t* out_host, int64_t n_words) {
   if (!h || !out_host) return fail(HK_E_INVALID, "hk_debug_lane_trace: NULL argument");
   if (!h->trace) return fail(HK_E_INVALID, "hk_debug_lane_trace: create the env with HK_LANE_TRACE=1");
-  const int64_t have = 16 * (h->n / 32 + 8) + 2 * h->n;
+  const int64_t have = 20 * (h->n / 32 + 8) + 2 * h->n;
   DeviceGuard guard(h->device);
   HK_CUDA(cudaMemcpy(out_host, h->trace, sizeof(uint32_t) * (size_t)(n_words < have ? n_words : have), cudaMemcpyDeviceToHost));
   return HK_OK;

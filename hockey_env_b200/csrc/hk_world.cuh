@@ -788,15 +788,27 @@ HK_HD_NOINLINE bool solveVelocityConstraint(Env& e, VC& vc) {
 // Either way the result is numerically identical to running all N sweeps, which is what the oracle does.
 // Specialised sweep loop for the dominant case -- one contact with one manifold point (95 % of solves): every
 // quantity lives in registers, same expression order as solveVelocityConstraint().
-HK_HD_NOINLINE int runVelocityIterations1Core(VC& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
+struct VC1 {  // what the one-point loop reads of a VC (64 B instead of 148: hk_lib.cu pools these in shared memory)
+  V2 rA, rB, normal;
+  float ni, ti, normalMass, tangentMass, bias, mA, iA, mB, iB, friction;
+};
+HK_HD VC1 vc1Of(const VC& vc) {
+  VC1 c;
+  c.rA = vc.pt[0].rA; c.rB = vc.pt[0].rB; c.normal = vc.normal;
+  c.ni = vc.pt[0].ni; c.ti = vc.pt[0].ti;
+  c.normalMass = vc.pt[0].normalMass; c.tangentMass = vc.pt[0].tangentMass; c.bias = vc.pt[0].bias;
+  c.mA = vc.mA; c.iA = vc.iA; c.mB = vc.mB; c.iB = vc.iB; c.friction = vc.friction;
+  return c;
+}
+HK_HD_NOINLINE int runVelocityIterations1Core(VC1& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
   int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   const V2 normal = vc.normal;
   const V2 tangent = cross(normal, 1.0f);
   const float friction = vc.friction;
-  const V2 rA = vc.pt[0].rA, rB = vc.pt[0].rB;
-  const float normalMass = vc.pt[0].normalMass, tangentMass = vc.pt[0].tangentMass, bias = vc.pt[0].bias;
-  float ni = vc.pt[0].ni, ti = vc.pt[0].ti;
+  const V2 rA = vc.rA, rB = vc.rB;
+  const float normalMass = vc.normalMass, tangentMass = vc.tangentMass, bias = vc.bias;
+  float ni = vc.ni, ti = vc.ti;
   V2 vA = A.v, vB = B.v;
   float wA = A.w, wB = B.w;
   // states after the previous sweep (1) and the one before (2)
@@ -858,8 +870,8 @@ HK_HD_NOINLINE int runVelocityIterations1Core(VC& vc, Vel& A, Vel& B, int budget
     }
     result = it + 1;
   }
-  vc.pt[0].ni = ni;
-  vc.pt[0].ti = ti;
+  vc.ni = ni;
+  vc.ti = ti;
   A.v = vA; A.w = wA; B.v = vB; B.w = wB;
   *sweepsOut = sweeps;
   return result;
@@ -867,7 +879,10 @@ HK_HD_NOINLINE int runVelocityIterations1Core(VC& vc, Vel& A, Vel& B, int budget
 HK_HD int runVelocityIterations1(Env& e, VC& vc, int velIters) {
   Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);
   int sweeps = 0;
-  const int result = runVelocityIterations1Core(vc, A, B, e.sweepBudget, velIters, &sweeps);
+  VC1 c = vc1Of(vc);
+  const int result = runVelocityIterations1Core(c, A, B, e.sweepBudget, velIters, &sweeps);
+  vc.pt[0].ni = c.ni;
+  vc.pt[0].ti = c.ti;
   storeVel(e, vc.bA, A);
   storeVel(e, vc.bB, B);
   e.nVelIters += (uint32_t)sweeps;

@@ -17,11 +17,11 @@ names = ("policy+collide", "solve", "toi-tasks", "toi-events")
 for rep in range(4):
     env.step()
     torch.cuda.synchronize()
-    buf = np.zeros(16 * nw + 2 * n, np.uint32)
+    buf = np.zeros(20 * nw + 2 * n, np.uint32)
     hk._lib.check(env.L.hk_debug_lane_trace(env._h, buf.ctypes.data, buf.size))
     w = buf[:4 * nw].reshape(nw, 4).astype(np.int64)
     rec = buf[4 * nw:4 * nw + 2 * n].reshape(n, 2)
-    blk = buf[4 * nw + 2 * n:].reshape(nw, 12).astype(np.int64)
+    blk = buf[4 * nw + 2 * n:].reshape(nw, 16).astype(np.int64)
     used = rec[:, 0] != 0
     r0 = rec[used, 0]
     gw = rec[used, 1]
@@ -63,6 +63,9 @@ for rep in range(4):
     print("  mean share per sub-phase: " + "  ".join(f"{bn[k]} {100 * busy[:, k].sum() / busy[:, 9].sum():.1f}%" for k in range(7)))
     for b in order[:6]:
         print(f"    slow block {b} (sm {blk[b, 7]}): total {blk[b, 9]}  " + "  ".join(f"{bn[k]} {blk[b, k]}" for k in range(7)) + f"  slowest solve unit: type {blk[b, 11]} {blk[b, 10]} cycles")
+    for lab, m in (("no env done", busy[:, 15] == 0), ("some env done", busy[:, 15] > 0)):
+        if m.any():
+            print(f"    finish phase, blocks with {lab} ({m.sum()}): phase {int(busy[m, 6].mean())}  max-warp cycles commit {int(busy[m, 12].mean())} tickFinish {int(busy[m, 13].mean())} store+stats {int(busy[m, 14].mean())}")
     ut = ("-", "2c(1,1)", "2c(1,2)", "2c(2,1)", "2c(2,2)", "3c(1,1,1)", "3c(1,1,2)", "3c(1,2,1)", "3c(2,1,1)", "1c2p chunk", "1c1p chunk", "in place")
     for k in range(1, 12):
         m = busy[:, 11] == k

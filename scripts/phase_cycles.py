@@ -1,6 +1,8 @@
 """Prints the share of block-cycles the general tiers spend in each tick phase (diagnostics)."""
 import ctypes as C
+import os
 import sys
+os.environ["HK_LANE_TRACE"] = "1"  # the per-lane TOI split is only collected when tracing
 import torch
 sys.path.insert(0, ".")
 import hockey_env_b200 as hk

@@ -26,7 +26,7 @@ def main():
     os.makedirs(PROF, exist_ok=True)
     pc = "phase_cycles.txt" if TAG == "r1_final" else "phase_cycles_%s.txt" % SHORT
     for src, dst in ((TAG + "_launches.csv", TAG + "_launches.csv"), ("bench_%s_final.json" % SHORT, SHORT + "_bench_1gpu.json"),
-                     ("bench_%s_131k.json" % SHORT, SHORT + "_bench_1gpu_131k_envs.json"),
+                     ("bench_%s_131k.json" % SHORT, SHORT + "_bench_1gpu_131k_envs.json"), ("bench_%s_32k.json" % SHORT, SHORT + "_bench_1gpu_32k_envs.json"),
                      ("bench_%s_1M.json" % SHORT, SHORT + "_bench_1gpu_1M_envs.json"), ("bench_%s_2gpu.json" % SHORT, SHORT + "_bench_2gpu.json"),
                      ("bench_%s_ref.json" % SHORT, SHORT + "_bench_reference_arm.json"), (pc, SHORT + "_phase_cycles.txt")):
         if os.path.exists(os.path.join(OUT, src)):

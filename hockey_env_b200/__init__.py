@@ -13,6 +13,7 @@ from .env import (  # noqa: F401
 
 from .vector import HockeyGymVectorEnv  # noqa: F401
 from .actor import ActorNetwork, actor_rollout, load_td3_actor  # noqa: F401
+from .training import DeviceReplayBuffer, OpponentPool, collect, evaluate  # noqa: F401
 
-__all__ = ["HockeyGymVectorEnv", "ActorNetwork", "actor_rollout", "load_td3_actor", "HockeyVecEnv", "HockeyEnv", "HockeyEnv_BasicOpponent", "BasicOpponent", "PolicyOpponent", "Mode",
+__all__ = ["OpponentPool", "DeviceReplayBuffer", "collect", "evaluate", "HockeyGymVectorEnv", "ActorNetwork", "actor_rollout", "load_td3_actor", "HockeyVecEnv", "HockeyEnv", "HockeyEnv_BasicOpponent", "BasicOpponent", "PolicyOpponent", "Mode",
            "HockeyLibraryError", "load_library"]

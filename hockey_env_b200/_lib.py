@@ -13,12 +13,12 @@ OBS_DIM, ACT_DIM, INFO_DIM, STATS_DIM = 18, 4, 4, 16
 N_PAIRS, CONTACT_WORDS = 27, 8
 STATE_WORDS = 64 + N_PAIRS * CONTACT_WORDS
 HK_OK, HK_E_INVALID, HK_E_CUDA, HK_E_NODEVICE = 0, -1, -2, -3
-POLICY_EXTERNAL, POLICY_BASIC_WEAK, POLICY_BASIC_STRONG, POLICY_RANDOM, POLICY_ZERO = 0, 1, 2, 3, 4
+POLICY_EXTERNAL, POLICY_BASIC_WEAK, POLICY_BASIC_STRONG, POLICY_RANDOM, POLICY_ZERO, POLICY_PER_ENV = 0, 1, 2, 3, 4, 5
 STEP_AUTORESET = 1
 
 EXPORTS = [
     "hk_create", "hk_destroy", "hk_num_envs", "hk_reset", "hk_step", "hk_rollout", "hk_get_obs", "hk_get_info", "hk_get_state",
-    "hk_set_state", "hk_set_obs_state", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_launches_per_step", "hk_debug_lane_trace", "hk_last_error",
+    "hk_set_state", "hk_set_obs_state", "hk_set_opponent_policies", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_launches_per_step", "hk_debug_lane_trace", "hk_last_error",
     "hk_version",
 ]
 
@@ -51,6 +51,8 @@ def load():
     L.hk_reset.restype = i32
     L.hk_step.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hk_step.restype = i32
+    L.hk_set_opponent_policies.argtypes = [vp, vp]
+    L.hk_set_opponent_policies.restype = i32
     L.hk_rollout.argtypes = [vp, i32, i32, i32, vp, vp]
     L.hk_rollout.restype = i32
     L.hk_get_obs.argtypes = [vp, vp, vp, vp]

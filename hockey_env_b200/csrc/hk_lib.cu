@@ -409,9 +409,9 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
       const float4* ab = reinterpret_cast<const float4*>(io.actBuf + 8 * i);
       float4 lo = ab[0], hi = ab[1];
       a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
-      policyAdvancePhases(P.cfg, e, env_id, io.pol1, io.pol2);
+      policyAdvancePhases(P.cfg, e, env_id, io.pol1, pol2Of(io, (size_t)i));
     } else {
-      policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+      policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, (size_t)i), a);
     }
     had1 = e.has1;
     had2 = e.has2;
@@ -837,6 +837,7 @@ struct hk_env {
   unsigned long long* phaseClk;
   float* actBuf;
   uint32_t* trace;
+  const uint8_t* pol2v = nullptr;  // hk_set_opponent_policies
   int tiers;  // HK_TIERS=2: fast + unlimited general tier; 3 (default): fast + budgeted + unlimited
   bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
@@ -950,6 +951,11 @@ struct hk_env {
 };
 
 static bool validPolicy(int p) { return p >= HK_POLICY_EXTERNAL && p <= HK_POLICY_ZERO; }
+
+__global__ void k_check_codes(const uint8_t* codes, int64_t n, int* bad) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && codes[i] > HK_POLICY_ZERO) atomicAdd(bad, 1);
+}
 
 extern "C" {
 
@@ -1091,19 +1097,25 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
             float* obs2_dev, float* reward_dev, float* reward2_dev, uint8_t* done_dev, float* info_dev, float* info2_dev,
             float* final_obs_dev, void* stream) {
   if (!h) return fail(HK_E_INVALID, "hk_step: NULL handle");
-  if (!validPolicy(p1_policy) || !validPolicy(p2_policy)) return fail(HK_E_INVALID, "hk_step: invalid policy id");
+  const bool perEnv = p2_policy == HK_POLICY_PER_ENV;
+  if (!validPolicy(p1_policy) || !(validPolicy(p2_policy) || perEnv)) return fail(HK_E_INVALID, "hk_step: invalid policy id");
+  if (perEnv && !h->pol2v) return fail(HK_E_INVALID, "hk_step: HK_POLICY_PER_ENV without hk_set_opponent_policies");
   if (!obs_dev) return fail(HK_E_INVALID, "hk_step: obs_dev is required");
   if ((p1_policy == HK_POLICY_EXTERNAL || p2_policy == HK_POLICY_EXTERNAL) && !action_dev)
     return fail(HK_E_INVALID, "hk_step: action_dev is NULL but a policy is EXTERNAL");
   if (p1_policy == HK_POLICY_EXTERNAL && action_stride < 4) return fail(HK_E_INVALID, "hk_step: action_stride < 4");
   if (p2_policy == HK_POLICY_EXTERNAL && action_stride < 8)
     return fail(HK_E_INVALID, "hk_step: player 2 EXTERNAL needs action_stride >= 8");
+  // per-env codes may contain EXTERNAL: those envs read columns 4..7
+  if (perEnv && (!action_dev || action_stride < 8))
+    return fail(HK_E_INVALID, "hk_step: HK_POLICY_PER_ENV needs action_dev with action_stride >= 8");
   DeviceGuard guard(h->device);
   StepIO io;
   io.action = action_dev;
   io.stride = action_stride;
   io.pol1 = p1_policy;
-  io.pol2 = p2_policy;
+  io.pol2 = perEnv ? HK_POLICY_ZERO : p2_policy;
+  io.pol2v = perEnv ? h->pol2v : nullptr;
   io.flags = flags;
   io.obs = obs_dev;
   io.obs2 = obs2_dev;
@@ -1122,6 +1134,24 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
     h->launchCascade(io, (cudaStream_t)stream);
   }
   HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+int hk_set_opponent_policies(hk_env* h, const uint8_t* codes_dev) {
+  if (!h) return fail(HK_E_INVALID, "hk_set_opponent_policies: NULL handle");
+  if (codes_dev) {  // one-time validation of the initial contents (later rewrites are the caller's responsibility)
+    DeviceGuard guard(h->device);
+    int* bad = nullptr;
+    int hostBad = 0;
+    HK_CUDA(cudaMalloc(&bad, sizeof(int)));
+    cudaMemset(bad, 0, sizeof(int));
+    k_check_codes<<<h->grid(), kBlock>>>(codes_dev, h->n, bad);
+    cudaError_t err = cudaMemcpy(&hostBad, bad, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(bad);
+    HK_CUDA(err);
+    if (hostBad) return fail(HK_E_INVALID, "hk_set_opponent_policies: codes must be HK_POLICY_EXTERNAL..HK_POLICY_ZERO");
+  }
+  h->pol2v = codes_dev;
   return HK_OK;
 }
 

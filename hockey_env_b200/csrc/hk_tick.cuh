@@ -11,6 +11,7 @@ struct StepIO {
   const float* action;  // [n, stride] or null
   int stride;
   int pol1, pol2, flags;
+  const uint8_t* pol2v;  // per-env player-2 policy codes (HK_POLICY_PER_ENV) or null
   float* obs;        // [n,18]
   float* obs2;       // [n,18] or null
   float* reward;     // [n] or null
@@ -22,6 +23,8 @@ struct StepIO {
   int write;         // 0: suppress all per-tick outputs (inner ticks of hk_rollout)
   float* actBuf;     // [n,8] scratch: clipped actions k_fast computed for the envs it hands to the general tiers
 };
+
+HK_HD int pol2Of(const StepIO& io, size_t i) { return io.pol2v ? (int)io.pol2v[i] : io.pol2; }
 
 struct TickStats {
   int episodes, wins, losses, draws, steps, len, touch1, touch2, velIters, toi, overflow;
@@ -110,7 +113,7 @@ HK_HD_NOINLINE void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64
 HK_HD bool envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e, uint64_t env_id, size_t i,
                    const StepIO& io, bool write, TickStats& st, int sweepBudget = 1 << 20, bool allowToiEvents = true) {
   float a[8];
-  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, i), a);
   const int had1 = e.has1, had2 = e.has2;
   e.sweepBudget = sweepBudget;
   e.allowToiEvents = allowToiEvents;
@@ -125,7 +128,7 @@ HK_HD bool envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e
 HK_HD bool envTickFast(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io,
                        bool write, TickStats& st) {
   float a[8];
-  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+  policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, i), a);
   const int had1 = e.has1, had2 = e.has2;
   if (!envStepFast(S, cfg, e, a)) {
     if (io.actBuf) {  // the general tier redoes the tick from the stored state; spare it the controllers
@@ -145,9 +148,9 @@ HK_HD bool envTickTouch(const Scene& S, const Config& cfg, const Cache& cache, E
   float a[8];
   if (pre) {
     for (int k = 0; k < 8; ++k) a[k] = pre[k];
-    policyAdvancePhases(cfg, e, env_id, io.pol1, io.pol2);
+    policyAdvancePhases(cfg, e, env_id, io.pol1, pol2Of(io, i));
   } else {
-    policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, io.pol2, a);
+    policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, i), a);
   }
   const int had1 = e.has1, had2 = e.has2;
   if (!envStepTouch(S, cfg, cache, e, a)) return false;

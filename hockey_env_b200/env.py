@@ -63,6 +63,7 @@ _POLICY_IDS = {
     "weak": _lib.POLICY_BASIC_WEAK, "basic_weak": _lib.POLICY_BASIC_WEAK,
     "strong": _lib.POLICY_BASIC_STRONG, "basic_strong": _lib.POLICY_BASIC_STRONG,
     "random": _lib.POLICY_RANDOM, "zero": _lib.POLICY_ZERO,
+    "per_env": _lib.POLICY_PER_ENV,  # player 2 only: one code per env (HockeyVecEnv.set_opponent_policies)
 }
 
 
@@ -89,6 +90,9 @@ class HockeyVecEnv:
     p1 / p2: None (actions come from the caller) or 'weak' / 'strong' (in-kernel BasicOpponent,
     hockey_env.py:781-833) / 'random' / 'zero'.  With p2 set, `step` takes [N,4] actions like
     HockeyEnv_BasicOpponent (hockey_env.py:875-886); otherwise [N,8] like HockeyEnv.
+    p2='per_env': every env has its own opponent code (`set_opponent_policies`), the batched form of drawing an
+    opponent per episode from a pool (rl/training/opponent_manager.py:62-91); `step` then takes [N,8] actions whose
+    columns 4..7 are only read by the envs whose code is 'external' (e.g. a self-play snapshot's output).
     """
 
     def __init__(self, num_envs, mode=Mode.NORMAL, keep_mode=True, device="cuda:0", seed=0, env_id_offset=0,
@@ -105,6 +109,9 @@ class HockeyVecEnv:
         self.auto_reset = bool(auto_reset)
         self.p1 = _policy_id(p1)
         self.p2 = _policy_id(p2)
+        if self.p1 == _lib.POLICY_PER_ENV:
+            raise ValueError("'per_env' is a player-2 policy")
+        self.opponent_codes = None
         self.want_agent_two = bool(want_agent_two)
         self.max_timesteps = 250 if self._mode == Mode.NORMAL else 80
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -126,6 +133,23 @@ class HockeyVecEnv:
             self.info2 = torch.empty((n, 4), dtype=torch.float32, device=d)
         with torch.cuda.device(self.device):
             _lib.check(self.L.hk_get_obs(self._h, _ptr(self.obs), _ptr(self.obs2), self._stream()))
+        if self.p2 == _lib.POLICY_PER_ENV:
+            self.set_opponent_policies(torch.full((n,), _lib.POLICY_BASIC_WEAK, dtype=torch.uint8, device=d))
+
+    def set_opponent_policies(self, codes):
+        """Per-env player-2 policy codes: uint8 CUDA tensor [N] of 0 external / 1 weak / 2 strong / 3 random / 4 zero
+        (or a list of policy names).  The tensor is kept and read by every step; rewrite `env.opponent_codes` in place
+        (e.g. `codes[done.bool()] = new`) to re-draw opponents for finished episodes without a host round trip."""
+        if not isinstance(codes, torch.Tensor):
+            codes = torch.tensor([_policy_id(c) for c in codes], dtype=torch.uint8)
+        codes = codes.to(device=self.device, dtype=torch.uint8).contiguous()
+        if codes.shape != (self.num_envs,):
+            raise ValueError("codes must be [num_envs]")
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            _lib.check(self.L.hk_set_opponent_policies(self._h, _ptr(codes)))
+        self.opponent_codes = codes
+        return codes
 
     # -- plumbing ---------------------------------------------------------------------------------
     def _stream(self):
@@ -179,7 +203,7 @@ class HockeyVecEnv:
         (player 1 only, player 2 in-kernel) or None (both in-kernel).  Returns the reference's 5-tuple of
         device tensors: obs [N,18], reward [N], done [N] (uint8), truncated [N] (all False), info dict."""
         a, stride = None, 0
-        if self.p1 == _lib.POLICY_EXTERNAL or self.p2 == _lib.POLICY_EXTERNAL:
+        if self.p1 == _lib.POLICY_EXTERNAL or self.p2 in (_lib.POLICY_EXTERNAL, _lib.POLICY_PER_ENV):
             if action is None:
                 raise ValueError("step() needs an action tensor: at least one player is external")
             a = action
@@ -188,6 +212,8 @@ class HockeyVecEnv:
             if a.dim() != 2 or a.shape[0] != self.num_envs:
                 raise ValueError(f"action must be [num_envs, 4 or 8], got {tuple(a.shape)}")
             stride = a.shape[1]
+            if self.p2 == _lib.POLICY_PER_ENV and stride != 8:
+                raise ValueError("p2='per_env' needs [num_envs, 8] actions (columns 4..7 for the external-opponent envs)")
             if self.p2 == _lib.POLICY_EXTERNAL and self.p1 != _lib.POLICY_EXTERNAL and stride == 4:
                 # only player 2 is external: its 4 columns are expected at offset 4
                 a = torch.cat([torch.zeros_like(a), a], dim=1).contiguous()

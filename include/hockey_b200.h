@@ -45,7 +45,8 @@ enum {
   HK_POLICY_BASIC_WEAK = 1,   /* in-kernel BasicOpponent(weak=True)  (hockey_env.py:781-833)         */
   HK_POLICY_BASIC_STRONG = 2, /* in-kernel BasicOpponent(weak=False)                                 */
   HK_POLICY_RANDOM = 3,       /* U(-1,1)^4 from Philox4x32-10 keyed (seed, global env id, tick)      */
-  HK_POLICY_ZERO = 4          /* all-zero action                                                     */
+  HK_POLICY_ZERO = 4,         /* all-zero action                                                     */
+  HK_POLICY_PER_ENV = 5       /* player 2 only: one of the codes above per env (hk_set_opponent_policies) */
 };
 
 /* ---- step flags ----------------------------------------------------------------------------- */
@@ -119,6 +120,14 @@ int hk_reset(hk_env* env, const uint8_t* mask_dev, const int8_t* one_starting_de
 int hk_step(hk_env* env, const float* action_dev, int action_stride, int p1_policy, int p2_policy, int flags,
             float* obs_dev, float* obs2_dev, float* reward_dev, float* reward2_dev, uint8_t* done_dev,
             float* info_dev, float* info2_dev, float* final_obs_dev, void* stream);
+
+/* Per-env opponent selection (the reference draws an opponent per episode from a pool: weak / strong
+ * BasicOpponent or a self-play snapshot, rl/training/opponent_manager.py:62-91, rl/training/self_play.py:7-68).
+ * codes_dev: n_envs bytes of HK_POLICY_EXTERNAL..HK_POLICY_ZERO, caller-owned device memory that must stay valid
+ * while p2_policy == HK_POLICY_PER_ENV is in use (it is read by every such hk_step; the caller may rewrite it
+ * between steps, e.g. for the envs that just finished an episode).  EXTERNAL envs read columns 4..7 of action_dev
+ * (a snapshot actor's output on obs_agent_two()); the others run their in-kernel controller.  NULL clears it. */
+int hk_set_opponent_policies(hk_env* env, const uint8_t* codes_dev);
 
 /* k_steps ticks with in-kernel policies (no EXTERNAL), autoreset on, enqueued back to back without any
  * per-tick output: only the last tick's obs (nullable) is written; episode statistics accumulate in

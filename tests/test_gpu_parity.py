@@ -361,3 +361,66 @@ def test_step_is_cuda_graph_capturable():
     assert len(state_mismatches(_state(a), _state(b))) == 0
     assert torch.equal(a.obs, b.obs) and torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done)
     assert a.stats()["env_steps"] == b.stats()["env_steps"]
+
+
+def test_per_env_opponent_policies_match_uniform_batches(oracle):
+    """hk_set_opponent_policies / HK_POLICY_PER_ENV: envs are independent and their RNG streams are keyed on the env
+    id, so env i of a mixed batch must equal env i of a uniform batch that runs env i's policy for everybody (the
+    uniform batches are the ones checked against the oracle above)."""
+    import torch
+    import hockey_env_b200 as hk
+    from hockey_env_b200 import _lib
+    from parity_util import state_mismatches
+    n, ticks = 2048, 260
+    names = ["weak", "strong", "random", "zero", "external"]
+    codes = torch.tensor([_lib.POLICY_BASIC_WEAK, _lib.POLICY_BASIC_STRONG, _lib.POLICY_RANDOM, _lib.POLICY_ZERO,
+                          _lib.POLICY_EXTERNAL], dtype=torch.uint8, device="cuda:0")[torch.arange(n, device="cuda:0") % 5]
+    mixed = hk.HockeyVecEnv(n, device="cuda:0", seed=77, p1="strong", p2="per_env")
+    mixed.set_opponent_policies(codes)
+    uniform = [hk.HockeyVecEnv(n, device="cuda:0", seed=77, p1="strong", p2=(None if nm == "external" else nm)) for nm in names]
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(5)
+    for t in range(ticks):
+        a2 = torch.rand((n, 4), device="cuda:0", generator=g) * 2 - 1
+        a8 = torch.cat([torch.zeros_like(a2), a2], dim=1).contiguous()
+        mixed.step(a8)
+        for nm, e in zip(names, uniform):
+            e.step(a2.contiguous() if nm == "external" else None)
+    sm = _state(mixed)
+    for k, e in enumerate(uniform):
+        rows = np.arange(k, n, 5)
+        assert len(state_mismatches(sm[rows], _state(e)[rows])) == 0, names[k]
+        assert torch.equal(mixed.obs[rows], e.obs[rows]) and torch.equal(mixed.reward[rows], e.reward[rows])
+    assert mixed.stats()["episodes"] > 0
+    bad = codes.clone()
+    bad[3] = 9
+    with pytest.raises(ValueError):  # HK_E_INVALID, like the reference's mode setter
+        mixed.set_opponent_policies(bad)
+
+
+def test_opponent_pool_replay_buffer_and_evaluator():
+    """The device-side training plumbing: per-episode opponent draws incl. a snapshot actor,
+    replay buffer fed from step outputs, and the Evaluator protocol against the in-kernel BasicOpponent."""
+    import torch
+    import hockey_env_b200 as hk
+    torch.manual_seed(0)
+    n = 1024
+    env = hk.HockeyVecEnv(n, device="cuda:0", seed=3, p2="per_env")
+    snap = hk.ActorNetwork().to("cuda:0").eval()
+    pool = hk.OpponentPool(env, p_weak=0.4, p_strong=0.4, snapshots=[snap], p_snapshot=0.2, seed=1)
+    frac = torch.bincount(pool.choice, minlength=3).float() / n
+    assert abs(frac[0] - 0.4) < 0.06 and abs(frac[1] - 0.4) < 0.06 and abs(frac[2] - 0.2) < 0.06
+    actor = hk.ActorNetwork().to("cuda:0").eval()
+    buf = hk.DeviceReplayBuffer(capacity=n * 64 + 100, device="cuda:0")
+    first = pool.choice.clone()
+    hk.collect(pool, actor, buf, steps=100)
+    assert len(buf) == n * 64 + 100 and buf.pos == (n * 100) % (n * 64 + 100)
+    o, a, r, no, d = buf.sample(512)
+    assert o.shape == (512, 18) and a.shape == (512, 4) and r.shape == (512,) and no.shape == (512, 18) and d.shape == (512,)
+    assert torch.isfinite(o).all() and torch.isfinite(no).all() and a.abs().max() <= 1.0
+    assert (pool.choice != first).any()  # episodes ended (a random actor loses quickly) and opponents were re-drawn
+    assert set(torch.unique(env.opponent_codes).tolist()) <= {0, 1, 2}
+    res = hk.evaluate(lambda obs: torch.zeros((obs.shape[0], 4), device=obs.device), n_episodes=300, opponent="weak",
+                      num_envs=512, seed=2)
+    assert res["episodes"] >= 300 and abs(res["win_rate"] + res["draw_rate"] + res["loss_rate"] - 1.0) < 1e-9
+    assert res["loss_rate"] > res["win_rate"]  # an idle player 1 against the weak BasicOpponent

@@ -1780,6 +1780,23 @@ HK_HD bool toiProvablySeparated(const Scene& S, const Env& e, int pid, int fA, i
   return gap > target + 0.25f * HK_LINEAR_SLOP + sag + 0.005f;
 }
 
+// The same first proof after a TOI event of body bi: every pair of that body that the event re-evaluated
+// (b2Contact::Update at the advanced pose) has a fresh separation bound, valid at pose (atC, atA).  The sub-step's
+// position correction moved the sweep start away from that pose by at most |dc| + R |da| (R <= 0.5 m), the rest of
+// the sweep approaches the static face by at most `disp` as above.
+HK_HD bool toiSeparatedAfterEvent(const Scene& S, const Env& e, int pid, int bi, float radiusB, V2 atC, float atA) {
+  const Body& B = e.b[bi];
+  const bool puck = bi == B_PUCK;
+  const V2 dc = B.c - B.c0;
+  const V2 sn = e.sepNormal[pid];
+  const float toward = (sn.x == 0.0f && sn.y == 0.0f) ? length(dc) : -dot(sn, dc);
+  const float disp = fmax2(toward, 0.0f) + (puck ? 0.0f : 0.5f * fabs2(B.a - B.a0));
+  const float corr = length(B.c0 - atC) + (puck ? 0.0f : 0.5f * fabs2(B.a0 - atA));
+  const float totalRadius = HK_POLYGON_RADIUS + radiusB;
+  const float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
+  return e.sepBound[pid] - corr - disp > target + 0.25f * HK_LINEAR_SLOP + 0.004f;
+}
+
 // One first-pass TOI evaluation as a self-contained task (hk_lib.cu runs these block-wide, one task per thread,
 // so that the lanes of a warp sit in b2TimeOfImpact together instead of one after the other).
 struct ToiTask {
@@ -1866,6 +1883,11 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
     toiCount[i] = 0;
   }
   e.toiPreFlag = 0;
+  // pairs whose separation bound the latest event refreshed (see toiSeparatedAfterEvent)
+  uint32_t freshMask = 0;
+  int freshBody = -1;
+  V2 freshC = mk(0.0f, 0.0f);
+  float freshA = 0.0f;
   for (;;) {
     int minPid = -1;
     float minAlpha = 1.0f;
@@ -1923,6 +1945,8 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
         // target + tolerance (+ margin) the answer is alpha = 1.
         bool skip = !e.toiEventSeen && alpha0 == 0.0f && ((solvedMask >> bi) & 1u) &&
                     toiProvablySeparated(S, e, pid, fA, bi, pB.radius);
+        if (!skip && bi == freshBody && (freshMask & bit) && e.sepBound[pid] != -HK_MAXFLOAT)
+          skip = toiSeparatedAfterEvent(S, e, pid, bi, pB.radius, freshC, freshA);
         HK_TOI_DBG(bi == B_PUCK ? 0 : 1);
         if (skip) {
           state = TOI_SEPARATED;
@@ -1972,6 +1996,10 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
     const float backupSA = salpha[sbA];
     salpha[sbA] = minAlpha;
     bodyAdvance(S, B, bi, minAlpha);
+    freshBody = bi;
+    freshC = B.c;
+    freshA = B.a;
+    freshMask = 1u << minPid;
     updateContact(S, cfg, cache, e, minPid);
     toiFlag &= ~(1u << minPid);
     ++toiCount[minPid];
@@ -1985,6 +2013,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
       B.a = backupB.a;
       B.alpha0 = backupB.alpha0;
       syncTransform(S, B, bi);
+      freshBody = -1;  // the body is back on its old sweep: the refreshed bounds do not describe its start
       continue;
     }
     setAwake(B, true);
@@ -2005,6 +2034,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
       float backup = salpha[so];
       if (!((staticIsland >> so) & 1u)) salpha[so] = minAlpha;
       updateContact(S, cfg, cache, e, pid);
+      freshMask |= bit;
       if (!(e.enabled & bit) || !(e.touch & bit)) {
         salpha[so] = backup;
         continue;

@@ -413,12 +413,13 @@ def test_opponent_pool_replay_buffer_and_evaluator():
     actor = hk.ActorNetwork().to("cuda:0").eval()
     buf = hk.DeviceReplayBuffer(capacity=n * 64 + 100, device="cuda:0")
     first = pool.choice.clone()
-    hk.collect(pool, actor, buf, steps=100)
-    assert len(buf) == n * 64 + 100 and buf.pos == (n * 100) % (n * 64 + 100)
+    hk.collect(pool, actor, buf, steps=260)  # > 250 ticks: every env finishes at least one episode
+    assert len(buf) == n * 64 + 100 and buf.pos == (n * 260) % (n * 64 + 100)
+    assert env.stats()["episodes"] >= n
     o, a, r, no, d = buf.sample(512)
     assert o.shape == (512, 18) and a.shape == (512, 4) and r.shape == (512,) and no.shape == (512, 18) and d.shape == (512,)
     assert torch.isfinite(o).all() and torch.isfinite(no).all() and a.abs().max() <= 1.0
-    assert (pool.choice != first).any()  # episodes ended (a random actor loses quickly) and opponents were re-drawn
+    assert (pool.choice != first).any()  # opponents were re-drawn for the finished episodes
     assert set(torch.unique(env.opponent_codes).tolist()) <= {0, 1, 2}
     res = hk.evaluate(lambda obs: torch.zeros((obs.shape[0], 4), device=obs.device), n_episodes=300, opponent="weak",
                       num_envs=512, seed=2)

@@ -421,7 +421,10 @@ def test_opponent_pool_replay_buffer_and_evaluator():
     assert torch.isfinite(o).all() and torch.isfinite(no).all() and a.abs().max() <= 1.0
     assert (pool.choice != first).any()  # opponents were re-drawn for the finished episodes
     assert set(torch.unique(env.opponent_codes).tolist()) <= {0, 1, 2}
-    res = hk.evaluate(lambda obs: torch.zeros((obs.shape[0], 4), device=obs.device), n_episodes=300, opponent="weak",
-                      num_envs=512, seed=2)
-    assert res["episodes"] >= 300 and abs(res["win_rate"] + res["draw_rate"] + res["loss_rate"] - 1.0) < 1e-9
-    assert res["loss_rate"] > res["win_rate"]  # an idle player 1 against the weak BasicOpponent
+    strong = hk.BasicOpponent(weak=False)  # vectorised on the obs tensor's device (hockey_env.py:787-833)
+    res = hk.evaluate(lambda obs: strong.act(obs).to(torch.float32), n_episodes=400, opponent="weak", num_envs=512, seed=2)
+    assert res["episodes"] >= 400 and abs(res["win_rate"] + res["draw_rate"] + res["loss_rate"] - 1.0) < 1e-9
+    assert res["win_rate"] > res["loss_rate"]  # strong BasicOpponent as player 1 against the weak one (notebook: ~2:1)
+    idle = hk.evaluate(lambda obs: torch.zeros((obs.shape[0], 4), device=obs.device), n_episodes=300, opponent="weak",
+                       num_envs=512, seed=2)
+    assert idle["episodes"] >= 300 and idle["win_rate"] == 0.0 and idle["mean_length"] > 100

@@ -440,7 +440,10 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     Solve1Task* s1tasks = reinterpret_cast<Solve1Task*>(sRaw + kRawMulti + sizeof(Solve2Task) * (size_t)cap2);
     // counts: multi kinds 1..8, one contact x 1 point, one contact x 2 points, all multi-contact slots handed out
     __shared__ int sKindCount[HK_MULTI_KINDS + 3];
+    __shared__ unsigned short sList[2][kSlowBlock];  // one-point tasks still unfinished after a round (double buffer)
+    __shared__ int sRound[5];                        // their count per round
     if (threadIdx.x < HK_MULTI_KINDS + 3) sKindCount[threadIdx.x] = 0;
+    if (threadIdx.x < 5) sRound[threadIdx.x] = 0;
     if (threadIdx.x == 0) sSlowUnit = 0;
     __syncthreads();
     stampB = clock64();
@@ -494,9 +497,17 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
       int c1 = (n1 + 31) >> 5;
       const int spare = nwarps - nm - c2;
       if (spare > c1) c1 = min(spare, (n1 + 3) >> 2);
-      const int units = nm + c2 + c1;
+      const int units = (phaseSync & 16) ? nm + c2 : nm + c2 + c1;
+      // Re-packed one-point rounds (phaseSync bit 4): 92 % of the one-point solves end within ~30 sweeps, 8 % creep to
+      // 180, so a chunk's lanes mostly idle behind its slowest one.  The warps that hold no multi-contact / two-point
+      // unit run the one-point tasks in rounds of sweeps [0,12) [12,24) [24,48) [48,180) and re-pack the unfinished
+      // tasks densely between rounds (exact: see runVelocityIterations1Range); they meet at a named barrier of their
+      // own while the other warps work through the heavy units.
+      const int wHeavy = !(phaseSync & 16) || units == 0 || nwarps == 1 ? 0 : min(units, max(1, nwarps / 2));
+      const int uStride = (phaseSync & 16) ? max(wHeavy, 1) : nwarps;
+      const bool heavyWarp = !(phaseSync & 16) || wib < wHeavy || nwarps == 1;
       // first round: unit w -> warp w; further rounds run backwards (the first warps hold the heavy multi-contact loops)
-      for (int r = 0, u = wib; u < units; ++r, u = r * nwarps + ((r & 1) ? nwarps - 1 - wib : wib)) {
+      for (int r = 0, u = wib; heavyWarp && u < units; ++r, u = r * uStride + ((r & 1) ? uStride - 1 - wib : wib)) {
         const long long tu0 = P.trace ? clock64() : 0;
         int utype = 10;  // diagnostics: 1..8 multi-contact shape, 9 two-point chunk, 10 one-point chunk, 11 in place
         if (u < nm) {
@@ -539,6 +550,37 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         }
         if (u >= nm && u < nm + c2) utype = 9;
         if (P.trace && lane == 0) atomicMax(&sSlowUnit, ((unsigned long long)(clock64() - tu0) << 8) | (unsigned)utype);
+      }
+      if ((phaseSync & 16) && wib >= wHeavy) {
+        const long long tu0 = P.trace ? clock64() : 0;
+        const int w1 = nwarps - wHeavy, myw = wib - wHeavy;
+        int nA = n1, it0 = 0;
+        for (int r = 0; r < 4 && nA > 0; ++r) {
+          const int stop = r == 0 ? 12 : (r == 1 ? 24 : (r == 2 ? 48 : 6 * 30));
+          const int chunks = (nA + 31) >> 5;
+          for (int ch = myw; ch < chunks; ch += w1) {
+            const int j = (ch << 5) + lane;
+            if (j < nA) {
+              const int idx = r == 0 ? j : (int)sList[r & 1][j];
+              Solve1Task& t = s1tasks[idx];
+              Vel A = t.A, B = t.B;
+              int sweeps = 0;
+              const int res = runVelocityIterations1Range(t.vc, A, B, budget, 6 * 30, it0, stop, &sweeps);
+              t.A = A;
+              t.B = B;
+              if (res == HK_SOLVE_UNFINISHED) {
+                sList[(r + 1) & 1][atomicAdd(&sRound[r + 1], 1)] = (unsigned short)idx;
+              } else {
+                t.result = res;
+                t.sweeps = it0 + sweeps;
+              }
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"r"(w1 * 32) : "memory");  // the one-point warps only
+          nA = sRound[r + 1];
+          it0 = stop;
+        }
+        if (P.trace && lane == 0) atomicMax(&sSlowUnit, ((unsigned long long)(clock64() - tu0) << 8) | 10u);
       }
     }
     int itc = 0;
@@ -929,10 +971,11 @@ struct hk_env {
   // carve-out that holds the blocks an SM will actually run (the driver's default sizes it for the register-limited
   // block count, which at small blocks leaves almost no L1).  HK_CARVEOUT=0 keeps the driver default.
   bool carveout = true;
+  size_t staticSmem = sizeof(Scene) + 2048;  // static shared memory of k_general (queried at creation)
   void shapeSharedMemory() const {
     if (!carveout) return;
     auto pct = [](size_t bytes) { return (int)std::min<size_t>(100, (bytes * 100 + 228 * 1024 - 1) / (228 * 1024)); };
-    const size_t stat = sizeof(Scene) + 256;
+    const size_t stat = staticSmem;
     const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
     cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? 1 : perSm1)));
     cudaFuncSetAttribute(k_fast, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 5));
@@ -1020,10 +1063,12 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     h->touch = n_envs >= 500000;
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
     if (const char* co = getenv("HK_CARVEOUT")) h->carveout = co[0] != '0';
-    h->phaseSync = 15;  // bit 3 (8): pool the single-contact solves too (phase 2)
-    if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 15;
+    h->phaseSync = 31;  // bit 3 (8): pool the single-contact solves too (phase 2); bit 4 (16): re-packed one-point rounds
+    if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 31;
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 16) sms = 148;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_general<1>) == cudaSuccess) h->staticSmem = fa.sharedSizeBytes;
     h->targetBlocks = sms;  // one general-tier block per SM in a single wave (measured: 148 > 140 > 132 on a 148-SM B200)
     h->shapeTier1();
     h->launches = h->mono ? 1 : 2 + (h->touch ? 1 : 0) + (h->tiers == 3 ? 1 : 0);

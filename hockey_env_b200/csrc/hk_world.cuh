@@ -800,7 +800,13 @@ HK_HD VC1 vc1Of(const VC& vc) {
   c.mA = vc.mA; c.iA = vc.iA; c.mB = vc.mB; c.iB = vc.iB; c.friction = vc.friction;
   return c;
 }
-HK_HD_NOINLINE int runVelocityIterations1Core(VC1& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
+// Sweeps [itStart, itStop) of the velIters-sweep solve; HK_SOLVE_UNFINISHED if it neither ended nor reached velIters.
+// The solve may be cut into such ranges anywhere (hk_lib.cu re-packs the lanes of its pooled solves between ranges):
+// a fixed point stays a fixed point, and a period-2 cycle found later is resolved by the parity of the ABSOLUTE sweep
+// index, so the result does not depend on the cuts.
+enum { HK_SOLVE_UNFINISHED = -2 };
+HK_HD_NOINLINE int runVelocityIterations1Range(VC1& vc, Vel& A, Vel& B, int budget, int velIters, int itStart, int itStop,
+                                               int* sweepsOut) {
   int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   const V2 normal = vc.normal;
@@ -814,9 +820,9 @@ HK_HD_NOINLINE int runVelocityIterations1Core(VC1& vc, Vel& A, Vel& B, int budge
   // states after the previous sweep (1) and the one before (2)
   V2 vA1 = vA, vB1 = vB, vA2 = vA, vB2 = vB;
   float wA1 = wA, wB1 = wB, ni1 = ni, ti1 = ti, wA2 = wA, wB2 = wB, ni2 = ni, ti2 = ti;
-  int it = 0;
-  int result = 0;
-  for (; it < velIters; ++it) {
+  int it = itStart;
+  int result = itStop < velIters ? (int)HK_SOLVE_UNFINISHED : 0;
+  for (; it < itStop; ++it) {
     bool changed = false;
     {
       V2 dv = vB + cross(wB, rB) - vA - cross(wA, rA);
@@ -852,7 +858,7 @@ HK_HD_NOINLINE int runVelocityIterations1Core(VC1& vc, Vel& A, Vel& B, int budge
       result = it + 1;
       break;
     }
-    if (it >= 2 && vA.x == vA2.x && vA.y == vA2.y && wA == wA2 && vB.x == vB2.x && vB.y == vB2.y && wB == wB2 &&
+    if (it >= itStart + 2 && vA.x == vA2.x && vA.y == vA2.y && wA == wA2 && vB.x == vB2.x && vB.y == vB2.y && wB == wB2 &&
         ni == ni2 && ti == ti2) {
       // period-2 cycle: state after sweep it+1 == state after sweep it-1
       const int remaining = velIters - 1 - it;
@@ -868,13 +874,16 @@ HK_HD_NOINLINE int runVelocityIterations1Core(VC1& vc, Vel& A, Vel& B, int budge
       result = -1;
       break;
     }
-    result = it + 1;
+    if (it + 1 == velIters) result = velIters;
   }
   vc.ni = ni;
   vc.ti = ti;
   A.v = vA; A.w = wA; B.v = vB; B.w = wB;
   *sweepsOut = sweeps;
   return result;
+}
+HK_HD int runVelocityIterations1Core(VC1& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
+  return runVelocityIterations1Range(vc, A, B, budget, velIters, 0, velIters, sweepsOut);
 }
 HK_HD int runVelocityIterations1(Env& e, VC& vc, int velIters) {
   Vel A = loadVel(e, vc.bA), B = loadVel(e, vc.bB);

@@ -18,4 +18,6 @@ python scripts/phase_cycles.py 65536 > $O/phase_cycles_$T.txt 2>&1; cat $O/phase
 CMD="python bench.py --steps 20 --warmup 100 --no-cpu-baseline --e2e-steps 5"
 $CMD > $O/plain_$T.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 120 --csv --log-file $O/${T}_launches.csv $CMD > $O/ncu_a_$T.log 2>&1
 $CMD > $O/plain_$T.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'k_general|k_fast' -s 220 -c 2 -f -o $O/${T}_full $CMD > $O/ncu_b_$T.log 2>&1
+CMD2="python bench.py --envs 1048576 --steps 6 --warmup 60 --no-cpu-baseline --e2e-steps 3"
+$CMD2 > $O/plain_${T}_1M.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 180 -c 18 --csv --log-file $O/${T}_launches_1M.csv $CMD2 > $O/ncu_c_$T.log 2>&1
 tail -2 $O/ncu_b_$T.log

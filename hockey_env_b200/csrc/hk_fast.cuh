@@ -44,6 +44,7 @@ HK_HD int bailClass(int kind) {
 template <bool PUCK_RACKET>
 HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   int i = 0;
+  const uint32_t ov = e.ncontacts > 0 ? pairOverlapBits(S, e) : 0u;  // proxies do not move during Collide
   while (i < e.ncontacts) {
     int pid = clistGet(e.clist, i);
     const uint32_t bit = 1u << pid;
@@ -57,7 +58,7 @@ HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, const Cache& 
       ++i;
       continue;
     }
-    if (!aabbOverlap(fixtureFat(S, e, fA), fixtureFat(S, e, fB))) {
+    if (!(ov & bit)) {
       clistRemoveAt(e, i);
       e.exist &= ~bit;
       e.touch &= ~bit;

@@ -258,6 +258,23 @@ HK_HD_NOINLINE void setTransformPuck(const Scene& S, Env& e, V2 position) {
   moveProxy(e, B_PUCK, comb, b.p - b.p);
 }
 
+// Fat-AABB overlap (b2TestOverlap) of all 27 candidate pairs at once, bit pid: straight-line code that is the same for
+// every lane (the pair table is known at compile time), instead of a per-lane walk over each lane's own candidates
+HK_HD uint32_t pairOverlapBits(const Scene& S, const Env& e) {
+  const AABB f0 = e.fat[0], f1 = e.fat[1], f2 = e.fat[2];
+  uint32_t ov = 0;
+#pragma unroll
+  for (int pid = 0; pid < N_PAIRS; ++pid) {
+    int fA = 0, fB = 0;
+    pairFixtures(pid, &fA, &fB);
+    const AABB a = fA < N_STATIC_FIX ? S.sfat[fA] : (fA == F_R1 ? f0 : f1);
+    const AABB b = fB == F_R1 ? f0 : (fB == F_R2 ? f1 : f2);
+    const bool apart = (b.lx - a.hx > 0.0f) || (b.ly - a.hy > 0.0f) || (a.lx - b.hx > 0.0f) || (a.ly - b.hy > 0.0f);
+    ov |= (apart ? 0u : 1u) << pid;
+  }
+  return ov;
+}
+
 // b2ContactManager::FindNewContacts for the buffered proxy moves
 HK_HD_NOINLINE void findNewContacts(const Scene& S, Env& e) {
   uint32_t mv = e.moved & 7u;
@@ -268,12 +285,8 @@ HK_HD_NOINLINE void findNewContacts(const Scene& S, Env& e) {
   if (mv & 2u) cand |= HK_PAIRS_R2;
   if (mv & 4u) cand |= HK_PAIRS_PUCK;
   cand &= ~e.exist;
-  uint32_t fresh = 0;
-  for (int pid = 0; pid < N_PAIRS; ++pid) {
-    if (!((cand >> pid) & 1u)) continue;
-    int fA = S.pairFA[pid], fB = S.pairFB[pid];
-    if (aabbOverlap(fixtureFat(S, e, fA), fixtureFat(S, e, fB))) fresh |= 1u << pid;
-  }
+  if (!cand) return;
+  const uint32_t fresh = pairOverlapBits(S, e) & cand;
   if (!fresh) return;
   for (int k = 0; k < N_PAIRS; ++k) {  // creation order = sorted (proxyA, proxyB); each goes to the list head
     int pid = S.sortedPairs[k];
@@ -476,6 +489,7 @@ HK_HD_NOINLINE void commitCache(const Cache& cache, const Env& e) {
 // b2ContactManager::Collide
 HK_HD_NOINLINE void collide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   int i = 0;
+  const uint32_t ov = e.ncontacts > 0 ? pairOverlapBits(S, e) : 0u;  // proxies do not move during Collide
   while (i < e.ncontacts) {
     int pid = clistGet(e.clist, i);
     int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
@@ -485,7 +499,7 @@ HK_HD_NOINLINE void collide(const Scene& S, const Config& cfg, const Cache& cach
       ++i;
       continue;
     }
-    if (!aabbOverlap(fixtureFat(S, e, S.pairFA[pid]), fixtureFat(S, e, S.pairFB[pid]))) {
+    if (!((ov >> pid) & 1u)) {
       clistRemoveAt(e, i);
       e.exist &= ~(1u << pid);
       e.touch &= ~(1u << pid);

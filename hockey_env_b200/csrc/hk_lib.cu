@@ -971,6 +971,7 @@ struct hk_env {
   // carve-out that holds the blocks an SM will actually run (the driver's default sizes it for the register-limited
   // block count, which at small blocks leaves almost no L1).  HK_CARVEOUT=0 keeps the driver default.
   bool carveout = true;
+  int fastBlock = kBlock;  // threads per block of k_fast / k_touch (HK_FAST_BLOCK: 32..128)
   size_t staticSmem = sizeof(Scene) + 2048;  // static shared memory of k_general (queried at creation)
   void shapeSharedMemory() const {
     if (!carveout) return;
@@ -984,8 +985,8 @@ struct hk_env {
   void launchCascade(const StepIO& io, cudaStream_t stream) const {
     shapeSharedMemory();
     if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (20 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
-    k_fast<<<grid(), kBlock, 0, stream>>>(params(), io);
-    if (touch) k_touch<<<grid(), kBlock, 0, stream>>>(params(), io);
+    k_fast<<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    if (touch) k_touch<<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     const int b2 = blockTier2(), w2 = b2 / 32;
     k_general<1><<<gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(
         params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
@@ -1063,6 +1064,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     h->touch = n_envs >= 500000;
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
     if (const char* co = getenv("HK_CARVEOUT")) h->carveout = co[0] != '0';
+    if (const char* fb = getenv("HK_FAST_BLOCK")) h->fastBlock = std::min(kBlock, std::max(32, atoi(fb) / 32 * 32));
     h->phaseSync = 31;  // bit 3 (8): pool the single-contact solves too (phase 2); bit 4 (16): re-packed one-point rounds
     if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 31;
     int sms = 148;

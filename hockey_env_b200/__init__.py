@@ -6,7 +6,7 @@ include/hockey_b200.h; this package is the thin host-side mirror of the referenc
 """
 from ._lib import HockeyLibraryError, load as load_library  # noqa: F401
 from .env import (  # noqa: F401
-    BasicOpponent, HockeyEnv, HockeyEnv_BasicOpponent, HockeyVecEnv, Mode, PolicyOpponent,
+    BasicOpponent, HockeyEnv, HockeyEnv_BasicOpponent, HockeyVecEnv, Mode, PolicyOpponent, REGISTRY, make, make_vec, spec,
     FPS, SCALE, VIEWPORT_W, VIEWPORT_H, W, H, CENTER_X, CENTER_Y, ZONE, MAX_ANGLE, MAX_TIME_KEEP_PUCK, GOAL_SIZE,
     RACKETPOLY, RACKETFACTOR, FORCEMULTIPLIER, SHOOTFORCEMULTIPLIER, TORQUEMULTIPLIER, MAX_PUCK_SPEED,
 )
@@ -15,5 +15,5 @@ from .vector import HockeyGymVectorEnv  # noqa: F401
 from .actor import ActorNetwork, actor_rollout, load_td3_actor  # noqa: F401
 from .training import DeviceReplayBuffer, OpponentPool, collect, evaluate  # noqa: F401
 
-__all__ = ["OpponentPool", "DeviceReplayBuffer", "collect", "evaluate", "HockeyGymVectorEnv", "ActorNetwork", "actor_rollout", "load_td3_actor", "HockeyVecEnv", "HockeyEnv", "HockeyEnv_BasicOpponent", "BasicOpponent", "PolicyOpponent", "Mode",
+__all__ = ["make", "make_vec", "spec", "REGISTRY", "OpponentPool", "DeviceReplayBuffer", "collect", "evaluate", "HockeyGymVectorEnv", "ActorNetwork", "actor_rollout", "load_td3_actor", "HockeyVecEnv", "HockeyEnv", "HockeyEnv_BasicOpponent", "BasicOpponent", "PolicyOpponent", "Mode",
            "HockeyLibraryError", "load_library"]

@@ -585,3 +585,50 @@ class PolicyOpponent:
             x = torch.tensor(obs, dtype=torch.float32, device=self.device).unsqueeze(0)
             a = self.policy(x).squeeze(0).cpu().numpy()
         return a
+
+
+# ---- env registry (hockey_env.py:889-903) ------------------------------------------------------------------------
+# The reference registers 'Hockey-v0' and 'Hockey-One-v0' with gymnasium; the same ids resolve here through make()
+# (and through gymnasium.make as well when gymnasium is installed), with the reference's default kwargs.
+REGISTRY = {
+    "Hockey-v0": ("HockeyEnv", {"mode": 0}),
+    "Hockey-One-v0": ("HockeyEnv_BasicOpponent", {"mode": 0, "weak_opponent": False}),
+}
+
+
+def spec(env_id):
+    """(class, default kwargs) registered under `env_id`."""
+    try:
+        name, kwargs = REGISTRY[env_id]
+    except KeyError:
+        raise ValueError(f"unknown env id {env_id!r}; registered: {sorted(REGISTRY)}")
+    return globals()[name], dict(kwargs)
+
+
+def make(env_id, **kwargs):
+    """gymnasium.make for the two registered ids: make('Hockey-One-v0', mode=Mode.TRAIN_DEFENSE, weak_opponent=True)."""
+    cls, defaults = spec(env_id)
+    defaults.update(kwargs)
+    return cls(**defaults)
+
+
+def make_vec(env_id, num_envs, **kwargs):
+    """Batched form of make(): the HockeyGymVectorEnv a SyncVectorEnv of `num_envs` such envs would be."""
+    from .vector import HockeyGymVectorEnv
+    cls, defaults = spec(env_id)
+    defaults.update(kwargs)
+    opponent = None
+    if cls is HockeyEnv_BasicOpponent:
+        opponent = "weak" if defaults.pop("weak_opponent", False) else "strong"
+    return HockeyGymVectorEnv(num_envs, mode=defaults.pop("mode", Mode.NORMAL), opponent=opponent, **defaults)
+
+
+try:  # optional: only when gymnasium is importable (it is not part of this image)
+    from gymnasium.envs.registration import register as _gym_register
+    for _id, (_name, _kw) in REGISTRY.items():
+        try:
+            _gym_register(id=_id, entry_point=f"hockey_env_b200.env:{_name}", kwargs=dict(_kw))
+        except Exception as _e:  # already registered (e.g. by the reference package)
+            pass
+except ImportError:
+    pass

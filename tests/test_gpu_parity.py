@@ -433,3 +433,20 @@ def test_opponent_pool_replay_buffer_and_evaluator():
     idle = hk.evaluate(lambda obs: torch.zeros((obs.shape[0], 4), device=obs.device), n_episodes=300, opponent="weak",
                        num_envs=512, seed=2)
     assert idle["episodes"] >= 300 and idle["win_rate"] == 0.0 and idle["mean_length"] > 100
+
+
+def test_registered_ids_make_and_make_vec():
+    """make('Hockey-One-v0', ...) / make_vec: the reference's gym ids (hockey_env.py:889-903) end to end."""
+    import hockey_env_b200 as hk
+    env = hk.make("Hockey-One-v0", mode=hk.Mode.TRAIN_SHOOTING, weak_opponent=True, seed=5)
+    obs, info = env.reset()
+    assert obs.shape == (18,) and env.action_space.shape == (4,)
+    for _ in range(5):
+        obs, r, done, trunc, info = env.step(np.zeros(4))
+    assert set(info) >= {"winner", "reward_closeness_to_puck", "reward_touch_puck", "reward_puck_direction"} and trunc is False
+    both = hk.make("Hockey-v0")
+    assert both.action_space.shape == (8,) and both.mode == hk.Mode.NORMAL
+    vec = hk.make_vec("Hockey-One-v0", 64, weak_opponent=True, seed=1)
+    o, i = vec.reset()
+    o, r, term, trunc, i = vec.step(np.zeros((64, 4), dtype=np.float32))
+    assert o.shape == (64, 18) and r.shape == (64,) and term.dtype == bool and "final_obs" in i

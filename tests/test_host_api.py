@@ -118,3 +118,19 @@ def test_basic_opponent_numpy_matches_oracle_controller(oracle):
                 np.random.uniform = orig
     out2 = b2.step(acts, O.POL_EXTERNAL, O.POL_EXTERNAL, 0)
     assert np.array_equal(out["obs"], out2["obs"])
+
+
+def test_registry_mirrors_the_reference_ids():
+    """hockey_env.py:889-903 registers 'Hockey-v0' (HockeyEnv, mode 0) and 'Hockey-One-v0' (HockeyEnv_BasicOpponent,
+    mode 0, strong opponent); make()/spec() resolve the same ids with the same defaults."""
+    import hockey_env_b200 as hk
+    cls, kw = hk.spec("Hockey-v0")
+    assert cls is hk.HockeyEnv and kw == {"mode": 0}
+    cls, kw = hk.spec("Hockey-One-v0")
+    assert cls is hk.HockeyEnv_BasicOpponent and kw == {"mode": 0, "weak_opponent": False}
+    with pytest.raises(ValueError):
+        hk.spec("Hockey-Two-v0")
+    import torch
+    if not torch.cuda.is_available():  # no CPU fallback: construction must fail loudly, not silently
+        with pytest.raises(hk.HockeyLibraryError):
+            hk.make("Hockey-v0")

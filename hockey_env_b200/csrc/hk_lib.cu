@@ -300,17 +300,14 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   extern __shared__ __align__(16) unsigned char sRaw[];  // phase 2: solve tasks; phase 3: TOI tasks + results (rawBytes())
   stageScene(&S);
   const int lane = threadIdx.x & 31;
-  // The first envWarps warps of a block carry envs; the others are helpers that only take part in the pooled phases
-  // (velocity solves, TOI evaluations).  A small batch leaves most of an SM's issue slots idle: helpers let its
-  // pooled work spread over more warps than it has env warps.
+  // Up to envWarps warps of a block carry envs (fewer in the blocks of the TOI-heavy work classes, see below); the
+  // others are helpers that only take part in the pooled phases (velocity solves, TOI evaluations).
   const int wib = threadIdx.x >> 5;
   bool envWarp = wib < envWarps;
   int64_t gw = (int64_t)blockIdx.x * envWarps + wib;  // global env-warp index (env warps only)
   const int envLanes = envWarps << 5;
-  // Only the first `lanes` lanes of a warp carry an env.  With small batches the general tiers are bound by
-  // per-warp latency (instruction fetch, local memory), not by issue slots: fewer envs per warp means fewer
-  // distinct control-flow paths to serialise and more warps in flight to hide the latency.
-  // lanesLog2 packs log2(envs per warp) of the four work classes, 3 bits each (tier 2: class 0's value)
+  // Only the first 2^l lanes of an env warp carry an env; lanesLog2 packs l for the four work classes, 3 bits each
+  // (tier 2: class 0's value).  Measured: full warps everywhere except 100k..200k envs (profiles/README.md).
   int cls = 0;
   bool valid = false;
   int64_t i = 0;

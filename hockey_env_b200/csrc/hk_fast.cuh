@@ -86,8 +86,7 @@ HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, const Cache& 
       Manifold m;
       collidePolygonCircle(&m, S.poly[fA], fixtureXf(S, e, fA), e.b[B_PUCK].p, S.puckRadius);
       if (m.count > 0) HK_BAIL(3 + (fA >= F_R1 ? 1 : 0));
-      e.sepBound[pid] = m.sepBound;
-      e.sepNormal[pid] = m.sepNormal;
+      setSep(e, pid, m.sepBound, m.sepNormal);
       touching = false;
     } else {
       if (bA >= 0) HK_BAIL(5);  // racket x racket: general path
@@ -95,8 +94,7 @@ HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, const Cache& 
       // rounding of this evaluation order against the one a real face separation would have
       V2 nrm;
       const float gap = polyStaticFaceGap(S, fA, S.poly[fB], bodyXf(e.b[bB]), &nrm);
-      e.sepBound[pid] = gap - 0.001f;
-      e.sepNormal[pid] = nrm;
+      setSep(e, pid, gap - 0.001f, nrm);
       if (gap > 2.0f * HK_POLYGON_RADIUS + 0.0005f) {
         touching = false;
       } else {
@@ -146,7 +144,7 @@ HK_HD_NOINLINE void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot 
 HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float h) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
-  for (int k = 0; k < N_PAIRS; ++k) e.sepBound[k] = -HK_MAXFLOAT;
+  e.sepValid = 0;
   if (e.moved & 8u) {
     e.moved &= ~8u;
     findNewContacts(S, e);
@@ -218,7 +216,7 @@ HK_HD_NOINLINE bool worldStepTouch(const Scene& S, const Config& cfg, const Cach
   e.nmf = 0;
   e.toiEventSeen = false;
   e.toiPreFlag = 0;
-  for (int k = 0; k < N_PAIRS; ++k) e.sepBound[k] = -HK_MAXFLOAT;
+  e.sepValid = 0;
   if (e.moved & 8u) {
     e.moved &= ~8u;
     findNewContacts(S, e);

@@ -87,7 +87,9 @@ struct Env {
   uint64_t pcount;        // 2 bits per pair: manifold point count held in the cache
   // per-step scratch
   uint32_t enabled;
-  float sepBound[N_PAIRS];  // per pair: distance lower bound from this tick's Collide (or -max if not evaluated)
+  uint32_t sepValid;        // pairs whose sepBound / sepNormal were evaluated this tick (one word instead of 27 resets:
+                            // every distinct local-memory word a warp touches costs a 128-byte L1 line)
+  float sepBound[N_PAIRS];  // per pair: distance lower bound from this tick's Collide (valid if its sepValid bit is set)
   V2 sepNormal[N_PAIRS];    // ... along this world-space face normal of the static polygon
   bool toiEventSeen;
   AABB swept[3];  // tight swept AABB (incl. shape radius) of each body from this tick's island solve
@@ -107,6 +109,14 @@ struct Env {
   bool aborted;
   int bailKind;  // why the fast path gave up (hk_fast.cuh)
 };
+
+HK_HD bool sepKnown(const Env& e, int pid) { return ((e.sepValid >> pid) & 1u) != 0; }
+HK_HD float sepBoundOf(const Env& e, int pid) { return sepKnown(e, pid) ? e.sepBound[pid] : -HK_MAXFLOAT; }
+HK_HD void setSep(Env& e, int pid, float bound, V2 normal) {
+  e.sepBound[pid] = bound;
+  e.sepNormal[pid] = normal;
+  e.sepValid |= 1u << pid;
+}
 
 struct Config {
   int mode, keep_mode, max_timesteps;
@@ -414,8 +424,7 @@ HK_HD_NOINLINE void updateContact(const Scene& S, const Config& cfg, const Cache
     int slot = findSlot(e, pid);
     Manifold tmp;
     evaluateManifold(S, e, pid, &tmp);
-    e.sepBound[pid] = tmp.sepBound;
-    e.sepNormal[pid] = tmp.sepNormal;  // statics have angle 0: local normal == world normal
+    setSep(e, pid, tmp.sepBound, tmp.sepNormal);  // statics have angle 0: local normal == world normal
     touching = tmp.count > 0;
     int oldCount;
     uint32_t oldKey[2] = {0, 0};
@@ -1760,13 +1769,15 @@ HK_HD float slantedFaceGap(const Scene& S, int f, const AABB& b) {
 HK_HD bool toiProvablySeparated(const Scene& S, const Env& e, int pid, int fA, int bi, float radiusB) {
   const Body& B = e.b[bi];
   V2 dc = B.c - B.c0;
-  const V2 sn = e.sepNormal[pid];
+  const bool known = sepKnown(e, pid);
+  const float sepB = known ? e.sepBound[pid] : -HK_MAXFLOAT;
+  const V2 sn = known ? e.sepNormal[pid] : mk(0.0f, 0.0f);
   // a zero normal marks a distance bound without a fixed direction: the whole displacement counts
   float toward = (sn.x == 0.0f && sn.y == 0.0f) ? length(dc) : -dot(sn, dc);
   float disp = fmax2(toward, 0.0f) + (bi == B_PUCK ? 0.0f : 0.5f * fabs2(B.a - B.a0));
   float totalRadius = HK_POLYGON_RADIUS + radiusB;
   float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
-  if (e.sepBound[pid] - disp > target + 0.25f * HK_LINEAR_SLOP + 0.002f) return true;
+  if (sepB - disp > target + 0.25f * HK_LINEAR_SLOP + 0.002f) return true;
   float da = fabs2(B.a - B.a0);
   if (bi != B_PUCK && da > 0.2f) return false;
   float sag = bi == B_PUCK ? 0.0f : 0.0625f * da * da;
@@ -1774,7 +1785,7 @@ HK_HD bool toiProvablySeparated(const Scene& S, const Env& e, int pid, int fA, i
   // n.p(t) = linear + |r| cos(theta(t) + phi), which stays above the lower of its two end values minus the
   // sagitta |r| da^2 / 8 (|r| <= 0.5 m) -- so the face separation during the sweep is at least
   // min(start, end) - sag.  The start value is sepBound; the end value is evaluated here from the final pose.
-  if (bi != B_PUCK && !(sn.x == 0.0f && sn.y == 0.0f) && e.sepBound[pid] > 0.0f) {
+  if (bi != B_PUCK && !(sn.x == 0.0f && sn.y == 0.0f) && sepB > 0.0f) {
     const Poly& PA = S.poly[fA];
     int k = -1;
     for (int i = 0; i < PA.count; ++i)
@@ -1788,7 +1799,7 @@ HK_HD bool toiProvablySeparated(const Scene& S, const Env& e, int pid, int fA, i
         V2 v = mul(xfB, polyV(PB, i));
         sEnd = fmin2(sEnd, sn.x * (v.x - px) + sn.y * (v.y - py));
       }
-      if (fmin2(e.sepBound[pid], sEnd) - sag - 0.001f > target + 0.25f * HK_LINEAR_SLOP + 0.002f) return true;
+      if (fmin2(sepB, sEnd) - sag - 0.001f > target + 0.25f * HK_LINEAR_SLOP + 0.002f) return true;
     }
   }
   // third proof (same as the fast tier): the swept core AABB of the body stays clear of the static core AABB
@@ -1817,7 +1828,7 @@ HK_HD bool toiSeparatedAfterEvent(const Scene& S, const Env& e, int pid, int bi,
   const float corr = length(B.c0 - atC) + (puck ? 0.0f : 0.5f * fabs2(B.a0 - atA));
   const float totalRadius = HK_POLYGON_RADIUS + radiusB;
   const float target = fmax2(HK_LINEAR_SLOP, totalRadius - 3.0f * HK_LINEAR_SLOP);
-  return e.sepBound[pid] - corr - disp > target + 0.25f * HK_LINEAR_SLOP + 0.004f;
+  return sepBoundOf(e, pid) - corr - disp > target + 0.25f * HK_LINEAR_SLOP + 0.004f;
 }
 
 // One first-pass TOI evaluation as a self-contained task (hk_lib.cu runs these block-wide, one task per thread,
@@ -1899,12 +1910,10 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
   e.b[0].island = e.b[1].island = e.b[2].island = false;
   e.b[0].alpha0 = e.b[1].alpha0 = e.b[2].alpha0 = 0.0f;
   uint32_t toiFlag = e.toiPreFlag;  // first-pass results computed ahead by the block-wide task pass (or 0)
-  float toi[N_PAIRS];
-  unsigned char toiCount[N_PAIRS];
-  for (int i = 0; i < N_PAIRS; ++i) {
-    toi[i] = ((toiFlag >> i) & 1u) ? e.toiPre[i] : 1.0f;
-    toiCount[i] = 0;
-  }
+  // cached alphas live in e.toiPre itself (its first-pass contents are only valid under toiFlag and dead after this
+  // function); the per-pair sub-step counters are 4-bit fields of two words -- no per-pair local arrays to reset
+  float* toi = e.toiPre;
+  uint64_t toiCountLo = 0, toiCountHi = 0;  // pairs 0-15 / 16-26
   e.toiPreFlag = 0;
   // pairs whose separation bound the latest event refreshed (see toiSeparatedAfterEvent)
   uint32_t freshMask = 0;
@@ -1918,7 +1927,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
       int pid = clistGet(e.clist, i);
       uint32_t bit = 1u << pid;
       if (!(e.enabled & bit)) continue;
-      if (toiCount[pid] > HK_MAX_SUBSTEPS) continue;
+      if ((int)(((pid < 16 ? toiCountLo : toiCountHi) >> (4 * (pid & 15))) & 15u) > HK_MAX_SUBSTEPS) continue;
       float alpha = 1.0f;
       if (toiFlag & bit) {
         alpha = toi[pid];
@@ -1968,7 +1977,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
         // target + tolerance (+ margin) the answer is alpha = 1.
         bool skip = !e.toiEventSeen && alpha0 == 0.0f && ((solvedMask >> bi) & 1u) &&
                     toiProvablySeparated(S, e, pid, fA, bi, pB.radius);
-        if (!skip && bi == freshBody && (freshMask & bit) && e.sepBound[pid] != -HK_MAXFLOAT)
+        if (!skip && bi == freshBody && (freshMask & bit) && sepKnown(e, pid))
           skip = toiSeparatedAfterEvent(S, e, pid, bi, pB.radius, freshC, freshA);
         HK_TOI_DBG(bi == B_PUCK ? 0 : 1);
         if (skip) {
@@ -1986,7 +1995,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
           HK_TOI_DBG(bi == B_PUCK ? 4 : 5);
           if (e.toiEventSeen) HK_TOI_DBG(6);
           else if (!(alpha0 == 0.0f && ((solvedMask >> bi) & 1u))) HK_TOI_DBG(7);
-          else if (e.sepBound[pid] == -HK_MAXFLOAT) HK_TOI_DBG(8);
+          else if (!sepKnown(e, pid)) HK_TOI_DBG(8);
           if (state == TOI_TOUCHING) HK_TOI_DBG(9);
         }
         float beta = t;
@@ -2025,7 +2034,7 @@ HK_HD_NOINLINE void solveTOI(const Scene& S, const Config& cfg, const Cache& cac
     freshMask = 1u << minPid;
     updateContact(S, cfg, cache, e, minPid);
     toiFlag &= ~(1u << minPid);
-    ++toiCount[minPid];
+    if (minPid < 16) toiCountLo += 1ull << (4 * minPid); else toiCountHi += 1ull << (4 * (minPid - 16));
     if (!(e.enabled & (1u << minPid)) || !(e.touch & (1u << minPid))) {
       e.enabled &= ~(1u << minPid);
       // restore sweeps (awake/sleep changes made by Update persist, as in b2World::SolveTOI)
@@ -2114,7 +2123,7 @@ HK_HD_NOINLINE void worldStepCollide(const Scene& S, const Config& cfg, const Ca
   e.nmf = 0;
   e.toiEventSeen = false;
   e.toiPreFlag = 0;
-  for (int k = 0; k < N_PAIRS; ++k) e.sepBound[k] = -HK_MAXFLOAT;
+  e.sepValid = 0;
   if (e.moved & 8u) {
     e.moved &= ~8u;
     findNewContacts(S, e);

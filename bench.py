@@ -28,11 +28,11 @@ ENVS_PER_GPU = 65536
 # written + obs 72 + reward 4 + done 1 + info 16 (in-kernel opponents: no action read)
 ALGO_BYTES_PER_ENV_STEP = 256 + 256 + 72 + 4 + 1 + 16
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_general<1>) for one launch at 65,536 envs, from the
-# `ncu --set full` capture summarised in profiles/r1d_raw_metrics.csv (45.3 MB read + 37.9 MB written)
-NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 = 83_226_112
-# smsp__inst_executed.sum of one tick at 65,536 envs from the same capture (k_fast 23.8 M + k_general 52.1 M warp
+# `ncu --set full` capture summarised in profiles/r1e_raw_metrics.csv (44.3 MB read + 33.8 MB written)
+NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 = 78_094_592
+# smsp__inst_executed.sum of one tick at 65,536 envs from the same capture (k_fast 22.4 M + k_general 51.6 M warp
 # instructions) and the issue ceiling of SURVEY.md section 8(d): 148 SMs x 4 schedulers x 1 warp-inst/clk x 1.965 GHz
-NCU_WARP_INST_PER_TICK_65536 = 23_828_147 + 52_078_319
+NCU_WARP_INST_PER_TICK_65536 = 22_403_347 + 51_615_094
 ISSUE_PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9
 
 
@@ -274,7 +274,7 @@ def main():
                          "issue": None if n != 65536 else {
                              "achieved": NCU_WARP_INST_PER_TICK_65536 / (kernel_ms / args.steps * 1e-3), "peak": ISSUE_PEAK_WARP_INST_PER_S,
                              "unit": "warp-inst/s", "frac": NCU_WARP_INST_PER_TICK_65536 / (kernel_ms / args.steps * 1e-3) / ISSUE_PEAK_WARP_INST_PER_S,
-                             "note": "warp instructions per tick from ncu (profiles/r1d_raw_metrics.csv) / measured tick time"},
+                             "note": "warp instructions per tick from ncu (profiles/r1e_raw_metrics.csv) / measured tick time"},
                          "note": "achieved = algorithmic bytes of one tick (all kernels of the cascade) / tick time; the path "
                                  "is instruction-fetch/divergence bound, not HBM-bound (DESIGN.md section 4, profiles/README.md)"},
             "episode_stats": {"episodes": st[0], "wins": st[1], "losses": st[2], "draws": st[3], "env_steps": st[4],

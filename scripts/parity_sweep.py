@@ -18,9 +18,9 @@ total, t0 = 0, time.time()
 for tiers in ("2", "3"):
     os.environ["HK_TIERS"] = tiers
     for mode, p1, p2 in ((0, 2, 2), (0, 1, 2), (0, 3, 3), (1, 3, 2), (1, 2, 3), (2, 2, 4), (2, 2, 1), (2, 3, 3)):
-        env = hk.HockeyVecEnv(n, mode=hk.Mode(mode), device="cuda:0", seed=100 + mode, env_id_offset=3 * 10 ** 9,
+        env = hk.HockeyVecEnv(n, mode=hk.Mode(mode), device="cuda:0", seed=int(os.environ.get("HK_SWEEP_SEED", "100")) + mode, env_id_offset=3 * 10 ** 9,
                               p1=names[p1], p2=names[p2], want_agent_two=True)
-        ora = O.OracleBatch(n, mode=mode, seed=100 + mode, env_id_offset=3 * 10 ** 9, n_threads=os.cpu_count() or 1)
+        ora = O.OracleBatch(n, mode=mode, seed=int(os.environ.get("HK_SWEEP_SEED", "100")) + mode, env_id_offset=3 * 10 ** 9, n_threads=os.cpu_count() or 1)
         ok = True
         for t in range(ticks):
             env.step()

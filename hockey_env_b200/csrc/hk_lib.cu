@@ -175,7 +175,10 @@ __global__ void __launch_bounds__(kBlock) k_step(KParams P, StepIO io) {
 // P.qctl = {count[0..3], tier-1 finished blocks, tier-2 count, tier-2 finished blocks, pad}.
 enum { Q_CLASSES = 4, QC_DONE1 = 4, QC_COUNT2 = 5, QC_DONE2 = 6 };
 
-__global__ void __launch_bounds__(kBlock) k_fast(KParams P, StepIO io) {
+// MINB = resident blocks per SM the register allocation aims at: 4 (120 registers, no spills) when the batch is one
+// wave anyway, 5 (96 registers) when occupancy pays (measured: profiles/README.md r1e)
+template <int MINB>
+__global__ void __launch_bounds__(kBlock, MINB) k_fast(KParams P, StepIO io) {
   __shared__ Scene S;
   stageScene(&S);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -976,13 +979,15 @@ struct hk_env {
     const size_t stat = staticSmem;
     const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
     cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? 1 : perSm1)));
-    cudaFuncSetAttribute(k_fast, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 5));
+    cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 4));
+    cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 5));
     cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 3));
   }
   void launchCascade(const StepIO& io, cudaStream_t stream) const {
     shapeSharedMemory();
     if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (20 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
-    k_fast<<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    if (n < 100000) k_fast<4><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    else k_fast<5><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     if (touch) k_touch<<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     const int b2 = blockTier2(), w2 = b2 / 32;
     k_general<1><<<gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(

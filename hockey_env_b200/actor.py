@@ -21,19 +21,29 @@ class ActorNetwork(nn.Module):
         return torch.tanh(self.fc3(x))
 
 
-def load_td3_actor(path, device="cuda:0"):
-    """Loads the `policy` entry of a reference checkpoint (`TD3Agent.save`, rl/td3/agent.py:269-275)."""
-    ckpt = torch.load(path, map_location=device)
-    sd = ckpt["policy"] if "policy" in ckpt else ckpt
-    actor = ActorNetwork().to(device)
-    # the reference names its layers l1/l2/l3 or fc1/fc2/fc3 depending on the run; map by order
-    keys = [k for k in sd.keys() if k.endswith("weight")]
-    if set(actor.state_dict().keys()) != set(sd.keys()) and len(keys) == 3:
-        ordered = sorted(sd.keys())
-        mapping = dict(zip(ordered, sorted(actor.state_dict().keys())))
-        sd = {mapping[k]: v for k, v in sd.items()}
+def load_td3_actor(path, device="cuda:0", name=None):
+    """The reference's trained policy as an on-device module.  `path` is either a reference checkpoint written by
+    `TD3Agent.save` (rl/td3/agent.py:269-275: a dict whose `policy` entry is the ActorNetwork state_dict) or an
+    `.npz` of float32 arrays `<name>.fc1.weight` ... `<name>.fc3.bias` (tests/golden/td3_actors.npz, extracted from
+    those checkpoints by tests/golden/make_actor_fixtures.py)."""
+    if str(path).endswith(".npz"):
+        import numpy as np
+        z = np.load(path)
+        names = sorted({k.split(".")[0] for k in z.files})
+        if name is None:
+            if len(names) != 1:
+                raise ValueError(f"{path} holds several actors {names}: pass name=")
+            name = names[0]
+        if name not in names:
+            raise ValueError(f"no actor {name!r} in {path}; have {names}")
+        sd = {k[len(name) + 1:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(name + ".")}
+    else:
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        sd = ckpt["policy"] if "policy" in ckpt else ckpt
+    hidden, obs_dim = sd["fc1.weight"].shape
+    actor = ActorNetwork(obs_dim=obs_dim, action_dim=sd["fc3.weight"].shape[0], hidden=hidden)
     actor.load_state_dict(sd)
-    return actor.eval()
+    return actor.to(device).eval()
 
 
 @torch.no_grad()

@@ -14,6 +14,7 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",  # no FMA contraction: bit-comparable with an SSE build of Box2D and with the oracle
     "-Xcompiler", "-fPIC", "-shared",
+    "--cudart", "shared",  # libcudart.so of the process (torch ships one): no second copy of the runtime in this library
 ]
 
 

@@ -209,8 +209,13 @@ HK_HD_NOINLINE void basicAct(const Config& cfg, const float* obs, bool weak, dou
 }
 
 // reset (hockey_env.py:345-418): overwrite per-env state; the scene itself is constant
-HK_HD double resetDraw(const Config& cfg, uint64_t env_id, uint32_t episode, int idx, double lo, double hi) {
-  U4 r = philox(cfg.seed, env_id, episode, (uint32_t)HK_STREAM_RESET | ((uint32_t)(idx >> 1) << 8));
+// reset_seed >= 0 (HockeyEnv.reset(seed=...), hockey_env.py:347 `self.seed(seed)`): the draws are a function of that seed
+// alone -- the same seed gives the same start state on any env of any batch; otherwise they come from the env's own
+// stream (library seed, global env id, episode counter)
+#define HK_SEEDED_RESET_TAG 0x5EEDED5EEDull
+HK_HD double resetDraw(const Config& cfg, uint64_t env_id, uint32_t episode, int64_t reset_seed, int idx, double lo, double hi) {
+  U4 r = reset_seed >= 0 ? philox((uint64_t)reset_seed, HK_SEEDED_RESET_TAG, 0u, (uint32_t)HK_STREAM_RESET | ((uint32_t)(idx >> 1) << 8))
+                         : philox(cfg.seed, env_id, episode, (uint32_t)HK_STREAM_RESET | ((uint32_t)(idx >> 1) << 8));
   double u = (idx & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
   return lo + (hi - lo) * u;
 }
@@ -236,7 +241,8 @@ HK_HD void createDynamicBody(const Scene& S, Env& e, int bi, double px, double p
   e.fat[bi].hx = a.hx + HK_AABB_EXTENSION;
   e.fat[bi].hy = a.hy + HK_AABB_EXTENSION;
 }
-HK_HD_NOINLINE void envReset(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, int one_starting /* -1 = alternate */) {
+HK_HD_NOINLINE void envReset(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, int one_starting /* -1 = alternate */,
+                             int64_t reset_seed = -1) {
   e.done = false;
   e.winner = 0;
   e.time = 0;
@@ -254,22 +260,22 @@ HK_HD_NOINLINE void envReset(const Scene& S, const Config& cfg, Env& e, uint64_t
   createDynamicBody(S, e, B_R1, HK_W / 5, HK_H / 2);
   int draw = 0;
   if (cfg.mode != 0) {
-    double dx = resetDraw(cfg, env_id, e.episode, draw++, -HK_W / 3, HK_W / 6);
-    double dy = resetDraw(cfg, env_id, e.episode, draw++, -HK_H / 4, HK_H / 4);
+    double dx = resetDraw(cfg, env_id, e.episode, reset_seed, draw++, -HK_W / 3, HK_W / 6);
+    double dy = resetDraw(cfg, env_id, e.episode, reset_seed, draw++, -HK_H / 4, HK_H / 4);
     createDynamicBody(S, e, B_R2, 4 * HK_W / 5 + dx, HK_H / 2 + dy);
   } else {
     createDynamicBody(S, e, B_R2, 4 * HK_W / 5, HK_H / 2);
   }
   if (cfg.mode == 0 || cfg.mode == 1) {
-    double dx = resetDraw(cfg, env_id, e.episode, draw++, HK_H / 8, HK_H / 4);
-    double dy = resetDraw(cfg, env_id, e.episode, draw++, -HK_H / 8, HK_H / 8);
+    double dx = resetDraw(cfg, env_id, e.episode, reset_seed, draw++, HK_H / 8, HK_H / 4);
+    double dy = resetDraw(cfg, env_id, e.episode, reset_seed, draw++, -HK_H / 8, HK_H / 8);
     if (e.one_starts || cfg.mode == 1) createDynamicBody(S, e, B_PUCK, HK_W / 2 - dx, HK_H / 2 + dy);
     else createDynamicBody(S, e, B_PUCK, HK_W / 2 + dx, HK_H / 2 + dy);
   } else {
-    double dx = resetDraw(cfg, env_id, e.episode, draw++, 0, HK_W / 3);
-    double dy = resetDraw(cfg, env_id, e.episode, draw++, -HK_H / 2, HK_H / 2);
+    double dx = resetDraw(cfg, env_id, e.episode, reset_seed, draw++, 0, HK_W / 3);
+    double dy = resetDraw(cfg, env_id, e.episode, reset_seed, draw++, -HK_H / 2, HK_H / 2);
     createDynamicBody(S, e, B_PUCK, HK_W / 2 + dx, HK_H / 2 + 0.8 * dy);
-    double ay = resetDraw(cfg, env_id, e.episode, draw++, -HK_GOAL_SIZE / HK_SCALE, HK_GOAL_SIZE / HK_SCALE);
+    double ay = resetDraw(cfg, env_id, e.episode, reset_seed, draw++, -HK_GOAL_SIZE / HK_SCALE, HK_GOAL_SIZE / HK_SCALE);
     Body& puck = e.b[B_PUCK];
     V2 direction = puck.p - mk(0.0f, (float)(HK_H / 2 + .6 * ay));
     float len = length(direction);

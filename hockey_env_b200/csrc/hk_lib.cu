@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kBlock) k_create(KParams P) {
   storeEnv(P.core, P.n, i, e);
 }
 
-__global__ void __launch_bounds__(kBlock) k_reset(KParams P, const uint8_t* mask, const int8_t* one_starting, float* obs) {
+__global__ void __launch_bounds__(kBlock) k_reset(KParams P, const uint8_t* mask, const int8_t* one_starting, const int64_t* seeds, float* obs) {
   __shared__ Scene S;
   stageScene(&S);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kBlock) k_reset(KParams P, const uint8_t* mask
   if (mask && !mask[i]) return;
   Env e;
   loadEnv(P.core, P.n, i, e);
-  envReset(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), one_starting ? (int)one_starting[i] : -1);
+  envReset(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), one_starting ? (int)one_starting[i] : -1, seeds ? seeds[i] : -1);
   storeEnv(P.core, P.n, i, e);
   if (obs) {
     float o[18];
@@ -866,6 +866,8 @@ __global__ void __launch_bounds__(kBlock) k_set_obs_state(KParams P, const float
 
 }  // namespace
 
+static long long g_shapedFor = -1;  // shapeKey() of the handle whose carve-out preferences are in force
+
 struct hk_env {
   int64_t n;
   int device;
@@ -880,7 +882,7 @@ struct hk_env {
   float* actBuf;
   uint32_t* trace;
   const uint8_t* pol2v = nullptr;  // hk_set_opponent_policies
-  int tiers;  // HK_TIERS=2: fast + unlimited general tier; 3 (default): fast + budgeted + unlimited
+  int tiers;  // HK_TIERS=2 (default): fast + unlimited general tier; 3: fast + budgeted + unlimited
   bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
     KParams P;
@@ -971,8 +973,11 @@ struct hk_env {
   // carve-out that holds the blocks an SM will actually run (the driver's default sizes it for the register-limited
   // block count, which at small blocks leaves almost no L1).  HK_CARVEOUT=0 keeps the driver default.
   bool carveout = true;
+  long long shapeKey() const { return carveout ? ((long long)device << 56) ^ ((long long)block1 << 40) ^ ((long long)classWarps1 << 44) ^ (long long)gridSlow(lanes1, envWarps1, classWarps1) : -2; }
   int fastBlock = kBlock;  // threads per block of k_fast / k_touch (HK_FAST_BLOCK: 32..128)
   size_t staticSmem = sizeof(Scene) + 2048;  // static shared memory of k_general (queried at creation)
+  // The carve-out preference is per-function, process-global state: it is set when a handle is created and again only
+  // when the previous launch came from a handle with another shape (two handles of different batch sizes in one process).
   void shapeSharedMemory() const {
     if (!carveout) return;
     auto pct = [](size_t bytes) { return (int)std::min<size_t>(100, (bytes * 100 + 228 * 1024 - 1) / (228 * 1024)); };
@@ -984,7 +989,10 @@ struct hk_env {
     cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 3));
   }
   void launchCascade(const StepIO& io, cudaStream_t stream) const {
-    shapeSharedMemory();
+    if (g_shapedFor != shapeKey()) {
+      shapeSharedMemory();
+      g_shapedFor = shapeKey();
+    }
     if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (20 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
     if (n < 100000) k_fast<4><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     else k_fast<5><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
@@ -1134,12 +1142,17 @@ int hk_destroy(hk_env* h) {
 
 int64_t hk_num_envs(const hk_env* h) { return h ? h->n : 0; }
 
-int hk_reset(hk_env* h, const uint8_t* mask_dev, const int8_t* one_starting_dev, float* obs_dev, void* stream) {
+int hk_reset_seeded(hk_env* h, const uint8_t* mask_dev, const int8_t* one_starting_dev, const int64_t* seeds_dev, float* obs_dev,
+                    void* stream) {
   if (!h) return fail(HK_E_INVALID, "hk_reset: NULL handle");
   DeviceGuard guard(h->device);
-  k_reset<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), mask_dev, one_starting_dev, obs_dev);
+  k_reset<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), mask_dev, one_starting_dev, seeds_dev, obs_dev);
   HK_CUDA(cudaGetLastError());
   return HK_OK;
+}
+
+int hk_reset(hk_env* h, const uint8_t* mask_dev, const int8_t* one_starting_dev, float* obs_dev, void* stream) {
+  return hk_reset_seeded(h, mask_dev, one_starting_dev, nullptr, obs_dev, stream);
 }
 
 int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy, int p2_policy, int flags, float* obs_dev,

@@ -180,22 +180,42 @@ class HockeyVecEnv:
                 "reward_puck_direction": info[:, 3]}
 
     # -- reference surface, batched ------------------------------------------------------------------
-    def reset(self, mask=None, one_starting=None):
+    def _per_env(self, value, dtype, name):
+        """A scalar (python or numpy, also 0-d) broadcast to [N], or a [N] array/tensor, as a contiguous device tensor."""
+        if isinstance(value, torch.Tensor):
+            t = value
+        else:
+            t = torch.as_tensor(np.asarray(value))
+        if t.dim() == 0:
+            return torch.full((self.num_envs,), t.item(), dtype=dtype, device=self.device)
+        if tuple(t.shape) != (self.num_envs,):
+            raise ValueError(f"{name} must be a scalar or have shape ({self.num_envs},), got {tuple(t.shape)}")
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def reset(self, mask=None, one_starting=None, seed=None):
         """HockeyEnv.reset (hockey_env.py:345-418) for the envs selected by `mask` (bool/uint8 [N], None = all).
-        one_starting: None = alternate like the reference, bool, or int8 tensor [N] (1/0/-1)."""
+        one_starting: None = alternate like the reference, a bool, or an int8 array/tensor [N] (1 / 0 / -1 = alternate).
+        seed: None = every env continues its own random stream; an int s = env i is reset with seed s + i (the
+        gymnasium vector convention); an int64 array/tensor [N] = one seed per env (negative = own stream).  A seeded
+        reset draws from that seed alone, like the reference's reseeding (hockey_env.py:347): same seed, same start."""
         m = None
         if mask is not None:
-            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            m = self._per_env(mask, torch.uint8, "mask")
         o = None
         if one_starting is not None:
-            if isinstance(one_starting, (bool, int)):
-                o = torch.full((self.num_envs,), int(bool(one_starting)), dtype=torch.int8, device=self.device)
+            o = self._per_env(one_starting, torch.int8, "one_starting")
+        sd = None
+        if seed is not None:
+            if isinstance(seed, (int, np.integer)) and not isinstance(seed, bool):
+                sd = (torch.arange(self.num_envs, dtype=torch.int64, device=self.device) + int(seed)) & 0x7FFFFFFFFFFFFFFF
             else:
-                o = torch.as_tensor(one_starting, device=self.device).to(torch.int8).contiguous()
+                sd = self._per_env(seed, torch.int64, "seed")
         with torch.cuda.device(self.device):
-            _lib.check(self.L.hk_reset(self._h, _ptr(m), _ptr(o), None, self._stream()))
+            _lib.check(self.L.hk_reset_seeded(self._h, _ptr(m), _ptr(o), _ptr(sd), None, self._stream()))
             _lib.check(self.L.hk_get_obs(self._h, _ptr(self.obs), _ptr(self.obs2), self._stream()))
             _lib.check(self.L.hk_get_info(self._h, _ptr(self.info), _ptr(self.info2), self._stream()))
+            if m is not None or o is not None or sd is not None:
+                torch.cuda.current_stream(self.device).synchronize()  # the argument tensors may be temporaries
         return self.obs, self._info_dict(self.info)
 
     def step(self, action=None):
@@ -398,6 +418,8 @@ class HockeyEnv(_EnvBase):
         self._mode = _as_mode(value)
 
     def seed(self, seed=None):
+        """hockey_env.py:157-160: the seed of the NEXT reset's draws (None = the env's own running stream)."""
+        self._seed = None if seed is None else int(seed) & 0x7FFFFFFFFFFFFFFF
         return [seed]
 
     def _obs_np(self, t):
@@ -414,7 +436,12 @@ class HockeyEnv(_EnvBase):
             raise ValueError("the mode of a HockeyEnv is fixed at construction in this implementation")
         if self._mode == Mode.NORMAL:
             self.one_starts = bool(one_starting) if one_starting is not None else (not self.one_starts)
-        self._vec.reset(one_starting=self.one_starts if self._mode == Mode.NORMAL else None)
+        if seed is not None:
+            self.seed(seed)
+        pending = getattr(self, "_seed", None)
+        self._seed = None
+        self._vec.reset(one_starting=self.one_starts if self._mode == Mode.NORMAL else None,
+                        seed=None if pending is None else torch.tensor([pending], dtype=torch.int64))
         self.done = False
         self.winner = 0
         self.time = 0
@@ -480,77 +507,55 @@ class HockeyEnv(_EnvBase):
 
 
 class BasicOpponent:
-    """hockey_env.py:781-833.  `act` accepts one observation (numpy, reference behaviour incl. the global
-    numpy RNG) or a batch [N,18] torch tensor (vectorised on the tensor's device)."""
+    """hockey_env.py:781-833: the scripted PD opponent.  `act` takes one observation (array-like [18], returns a numpy
+    float64 action like the reference and advances `phase` with the global numpy RNG as the reference does) or a batch
+    (torch tensor [N,18], returns a float32 tensor [N,4] on the same device; per-env phases, torch RNG).  Both go
+    through one vectorised controller; inside `HockeyVecEnv` the same rule runs in the step kernel (p1/p2='weak'|'strong')."""
+
+    # per-axis gains relative to kp and braking horizons of the (x, y, angle) PD loop (hockey_env.py:799-801,826-829)
+    _KP_SCALE = (1.0, 1.0 / 5, 1.0 / 2)
+    _BRAKE_HORIZON = (0.1, 0.1, 1.0)
 
     def __init__(self, weak=True, keep_mode=True):
         self.weak = weak
         self.keep_mode = keep_mode
         self.phase = np.random.uniform(0, np.pi)
 
+    def _controller(self, o, phase):
+        """o: float64 [N,18], phase: float64 [N] (already advanced) -> float64 [N,3 or 4]."""
+        kp, kd = (0.5 if self.weak else 10.0), 0.5
+        me, vel = o[:, 0:3], o[:, 3:6]
+        puck_x, puck_y, puck_vx, puck_vy = o[:, 12], o[:, 13], o[:, 14], o[:, 15]
+        home_x = torch.full_like(puck_x, -210 / SCALE)
+        incoming = puck_vx < 30.0 / SCALE                      # puck not moving away fast: track it, else go home
+        in_reach = (me[:, 0] < puck_x) & ((me[:, 1] - puck_y).abs() < 30.0 / SCALE)
+        gap = torch.sqrt((me[:, 0] - puck_x) ** 2 + (me[:, 1] - puck_y) ** 2)
+        goal_x = torch.where(incoming & in_reach, puck_x + 0.2, home_x)
+        goal_y = torch.where(incoming, torch.where(in_reach, puck_y + puck_vy * gap * 0.1, puck_y), torch.zeros_like(puck_y))
+        goal = torch.stack([goal_x, goal_y, MAX_ANGLE * torch.sin(phase)], 1)
+        err = goal - me
+        gains = torch.tensor(self._KP_SCALE, dtype=o.dtype, device=o.device) * kp
+        horizon = torch.tensor(self._BRAKE_HORIZON, dtype=o.dtype, device=o.device)
+        brake = ((err / (vel + 0.01)).abs() < horizon).to(o.dtype)
+        out = torch.clamp(err * gains - vel * brake * kd, -1, 1)
+        if self.keep_mode:
+            shoot = ((o[:, 16] > 0) & (o[:, 16] < 7)).to(o.dtype)
+            out = torch.cat([out, shoot[:, None]], 1)
+        return out
+
     def act(self, obs, verbose=False):
         if isinstance(obs, torch.Tensor) and obs.dim() == 2:
             return self._act_batch(obs)
-        obs = np.asarray(obs, dtype=np.float64)
-        alpha = obs[2]
-        p1 = np.asarray([obs[0], obs[1], alpha])
-        v1 = np.asarray(obs[3:6])
-        puck = np.asarray(obs[12:14])
-        puckv = np.asarray(obs[14:16])
-        target_pos = p1[0:2]
+        o = torch.as_tensor(np.asarray(obs, dtype=np.float64)).reshape(1, -1)
         self.phase += np.random.uniform(0, 0.2)
-        time_to_break = 0.1
-        kp = 0.5 if self.weak else 10
-        kd = 0.5
-        if puckv[0] < 30.0 / SCALE:
-            dist = np.sqrt(np.sum((p1[0:2] - puck) ** 2))
-            if p1[0] < puck[0] and abs(p1[1] - puck[1]) < 30.0 / SCALE:
-                target_pos = [puck[0] + 0.2, puck[1] + puckv[1] * dist * 0.1]
-            else:
-                target_pos = [-210 / SCALE, puck[1]]
-        else:
-            target_pos = [-210 / SCALE, 0]
-        target_angle = MAX_ANGLE * np.sin(self.phase)
-        shoot = 0.0
-        if self.keep_mode and obs[16] > 0 and obs[16] < 7:
-            shoot = 1.0
-        target = np.asarray([target_pos[0], target_pos[1], target_angle])
-        error = target - p1
-        with np.errstate(divide="ignore", invalid="ignore"):
-            need_break = abs((error / (v1 + 0.01))) < [time_to_break, time_to_break, time_to_break * 10]
-        action = np.clip(error * [kp, kp / 5, kp / 2] - v1 * need_break * [kd, kd, kd], -1, 1)
-        if self.keep_mode:
-            return np.hstack([action, [shoot]])
-        return action
+        return self._controller(o, torch.tensor([float(self.phase)], dtype=torch.float64))[0].numpy()
 
     def _act_batch(self, obs):
         n = obs.shape[0]
-        o = obs.to(torch.float64)
         if not isinstance(self.phase, torch.Tensor) or self.phase.shape[0] != n:
             self.phase = torch.rand(n, dtype=torch.float64, device=obs.device) * math.pi
         self.phase = self.phase + torch.rand(n, dtype=torch.float64, device=obs.device) * 0.2
-        kp = 0.5 if self.weak else 10.0
-        kd = 0.5
-        p1 = o[:, 0:3]
-        v1 = o[:, 3:6]
-        puck = o[:, 12:14]
-        puckv = o[:, 14:16]
-        dist = torch.sqrt(((p1[:, 0:2] - puck) ** 2).sum(1))
-        toward = puckv[:, 0] < 30.0 / SCALE
-        behind = (p1[:, 0] < puck[:, 0]) & ((p1[:, 1] - puck[:, 1]).abs() < 30.0 / SCALE)
-        tx = torch.where(toward & behind, puck[:, 0] + 0.2, torch.full_like(dist, -210 / SCALE))
-        ty = torch.where(toward, torch.where(behind, puck[:, 1] + puckv[:, 1] * dist * 0.1, puck[:, 1]), torch.zeros_like(dist))
-        ta = MAX_ANGLE * torch.sin(self.phase)
-        target = torch.stack([tx, ty, ta], 1)
-        error = target - p1
-        ttb = torch.tensor([0.1, 0.1, 1.0], dtype=torch.float64, device=obs.device)
-        need_break = ((error / (v1 + 0.01)).abs() < ttb).to(torch.float64)
-        kps = torch.tensor([kp, kp / 5, kp / 2], dtype=torch.float64, device=obs.device)
-        action = torch.clamp(error * kps - v1 * need_break * kd, -1, 1)
-        if self.keep_mode:
-            shoot = ((o[:, 16] > 0) & (o[:, 16] < 7)).to(torch.float64)
-            action = torch.cat([action, shoot[:, None]], 1)
-        return action.to(torch.float32)
+        return self._controller(obs.to(torch.float64), self.phase).to(torch.float32)
 
 
 class HockeyEnv_BasicOpponent(HockeyEnv):
@@ -574,17 +579,19 @@ class HockeyEnv_BasicOpponent(HockeyEnv):
 
 
 class PolicyOpponent:
-    """hockey_env.py:908-922: wraps a torch policy as act(obs) -> np.array of 4 actions."""
+    """hockey_env.py:908-922: adapts a torch policy to the opponent protocol `act(obs) -> action`.  One observation
+    (array-like [18]) gives a numpy action like the reference; a batch tensor [N,18] gives a tensor on its device."""
 
     def __init__(self, policy, device=None):
         self.policy = policy
         self.device = device
 
+    @torch.no_grad()
     def act(self, obs):
-        with torch.no_grad():
-            x = torch.tensor(obs, dtype=torch.float32, device=self.device).unsqueeze(0)
-            a = self.policy(x).squeeze(0).cpu().numpy()
-        return a
+        if isinstance(obs, torch.Tensor) and obs.dim() == 2:
+            return self.policy(obs.to(dtype=torch.float32, device=self.device or obs.device))
+        row = torch.as_tensor(np.asarray(obs), dtype=torch.float32, device=self.device)[None]
+        return self.policy(row)[0].cpu().numpy()
 
 
 # ---- env registry (hockey_env.py:889-903) ------------------------------------------------------------------------

@@ -9,7 +9,9 @@ The dense networks are plain torch modules (library matmuls): they are the ops n
 * `DeviceReplayBuffer`  ring buffer in HBM fed straight from step outputs (rl/replay/base_buffer.py:21-41,
                         rl/replay/uniform_buffer.py) -- `push` is one batched copy per tick instead of N Python calls
 * `evaluate`            the Evaluator protocol (rl/utils/evaluator.py:10-35): win / draw / loss rates and mean return
-                        of a policy against a fixed opponent over n episodes, from the on-device statistics
+                        of a policy against a fixed opponent over n COMPLETE episodes (fixed quota per env)
+* `evaluate_model`      the ModelEvaluator protocol (model_evaluation/model_evaluator.py:81-108): 300 episodes, seed
+                        123, against the weak and the strong BasicOpponent
 """
 import torch
 
@@ -140,18 +142,55 @@ def collect(pool_or_env, actor, buffer, steps):
 @torch.no_grad()
 def evaluate(actor, n_episodes=1000, opponent="strong", mode=Mode.NORMAL, num_envs=4096, device="cuda:0", seed=0,
              max_ticks=100000):
-    """Evaluator.evaluate (rl/utils/evaluator.py:10-35): plays until `n_episodes` episodes have finished against the
-    in-kernel weak/strong BasicOpponent and returns win/draw/loss rates, mean return and mean episode length, read
-    from the statistics the step kernels accumulate on the device.  `actor` maps obs [N,18] -> actions [N,4]."""
+    """Evaluator.evaluate (rl/utils/evaluator.py:10-35) batched: `actor` (obs [N,18] -> actions [N,4]) plays COMPLETE
+    episodes of Hockey-One-v0 against the in-kernel weak/strong BasicOpponent; returns the win rate (`winner == 1`) and
+    the mean return (sum of step rewards) the reference reports, plus draw/loss rates and the mean episode length.
+
+    Every env plays the same quota of k = ceil(n_episodes / num_envs) complete episodes and only those are counted (an
+    env that has filled its quota keeps stepping but is ignored), so k * num_envs >= n_episodes episodes are played --
+    stopping all envs once a global count is reached would keep only the shortest episodes and lose the 251-tick
+    draws.  Sides alternate like the reference's reset (hockey_env.py:359-362): even envs start with player 1."""
     env = HockeyVecEnv(num_envs, mode=mode, device=device, seed=seed, p2=opponent)
-    obs, ticks = env.obs, 0
+    n = env.num_envs
+    k = -(-int(n_episodes) // n)
+    dev = env.device
+    obs, _ = env.reset(one_starting=(torch.arange(n, device=dev) % 2 == 0).to(torch.int8))
+    count = torch.zeros(n, dtype=torch.int64, device=dev)
+    ret = torch.zeros(n, dtype=torch.float64, device=dev)
+    length = torch.zeros(n, dtype=torch.int64, device=dev)
+    acc = torch.zeros(6, dtype=torch.float64, device=dev)  # wins, draws, losses, sum return, sum return^2, sum length
+    ticks = 0
     while ticks < max_ticks:
-        obs, *_ = env.step(actor(obs).contiguous())
+        obs, reward, done, _, info = env.step(actor(obs).contiguous())
         ticks += 1
-        if ticks % 32 == 0 and env.stats()["episodes"] >= n_episodes:  # one small host read every 32 ticks
+        ret += reward.to(torch.float64)
+        length += 1
+        fin = done.to(torch.bool) & (count < k)
+        w = info["winner"]
+        f64 = fin.to(torch.float64)
+        acc += torch.stack([(f64 * (w == 1)).sum(), (f64 * (w == 0)).sum(), (f64 * (w == -1)).sum(), (f64 * ret).sum(),
+                            (f64 * ret * ret).sum(), (f64 * length).sum()])
+        count += fin
+        ret = torch.where(done.to(torch.bool), torch.zeros_like(ret), ret)
+        length = torch.where(done.to(torch.bool), torch.zeros_like(length), length)
+        if ticks % 16 == 0 and bool((count >= k).all().item()):  # one small host read every 16 ticks
             break
-    s = env.stats()
     env.close()
-    n = max(s["episodes"], 1)
-    return {"episodes": int(s["episodes"]), "win_rate": s["wins"] / n, "draw_rate": s["draws"] / n, "loss_rate": s["losses"] / n,
-            "mean_return": s["sum_return_p1"] / n, "mean_length": s["sum_episode_len"] / n, "ticks": ticks}
+    a = acc.cpu().tolist()
+    m = max(int(count.sum().item()), 1)
+    mean_ret = a[3] / m
+    return {"episodes": m, "win_rate": a[0] / m, "draw_rate": a[1] / m, "loss_rate": a[2] / m, "mean_return": mean_ret,
+            "std_return": max(a[4] / m - mean_ret * mean_ret, 0.0) ** 0.5, "mean_length": a[5] / m, "ticks": ticks,
+            "episodes_per_env": k}
+
+
+@torch.no_grad()
+def evaluate_model(actor, episodes=300, seed=123, num_envs=None, device="cuda:0"):
+    """ModelEvaluator._eval_once for both opponents (model_evaluation/model_evaluator.py:81-108, defaults :234-235:
+    300 complete episodes, seed 123): win rate and mean return of `actor` on Hockey-One-v0 against the weak and the
+    strong BasicOpponent -- the four numbers of one row of the reference's final-evaluation table."""
+    n = int(num_envs) if num_envs else int(episodes)
+    weak = evaluate(actor, n_episodes=episodes, opponent="weak", num_envs=n, device=device, seed=seed)
+    strong = evaluate(actor, n_episodes=episodes, opponent="strong", num_envs=n, device=device, seed=seed)
+    return {"wr_weak": weak["win_rate"], "wr_strong": strong["win_rate"], "ret_weak": weak["mean_return"],
+            "ret_strong": strong["mean_return"], "episodes": weak["episodes"]}

@@ -109,6 +109,12 @@ int64_t hk_num_envs(const hk_env* env);
  * reference does when one_starting is None (hockey_env.py:359-362) (NULL = alternate).
  * obs_dev [n,18] f32 (nullable) receives the post-reset observation. */
 int hk_reset(hk_env* env, const uint8_t* mask_dev, const int8_t* one_starting_dev, float* obs_dev, void* stream);
+/* HockeyEnv.reset(seed=...) (hockey_env.py:347 `self.seed(seed)`: the reference reseeds its generator on every reset, so
+ * the reset draws are a function of the seed alone; rl/utils/evaluator.py:18 relies on it with seed = agent.seed + i).
+ * seeds_dev: n_envs int64 (nullable); seeds_dev[i] >= 0 = that env's reset draws come from Philox keyed on this seed only
+ * (same seed -> same start state on any env of any batch); < 0 = the env's own stream as in hk_reset. */
+int hk_reset_seeded(hk_env* env, const uint8_t* mask_dev, const int8_t* one_starting_dev, const int64_t* seeds_dev,
+                    float* obs_dev, void* stream);
 
 /* Replaces HockeyEnv.step / HockeyEnv_BasicOpponent.step (hockey_env.py:658-695, :882-886).
  * action_dev: f32 [n, action_stride]; player 1 reads columns 0..3 when p1_policy is EXTERNAL,

@@ -164,9 +164,11 @@ struct Env {
   }
 
   const double* forced_draws = nullptr;  // tests: replace the reset draws (values, in draw order)
+  int64_t reset_seed = -1;  // >= 0: reset(seed=...) (hockey_env.py:347): the draws depend on this seed alone
   double r_uniform(double lo, double hi, int idx) {
     if (forced_draws) return forced_draws[idx];
-    U4 r = philox(seed, env_id, episode, (uint32_t)STREAM_RESET | ((uint32_t)(idx >> 1) << 8));
+    U4 r = reset_seed >= 0 ? philox((uint64_t)reset_seed, 0x5EEDED5EEDull, 0u, (uint32_t)STREAM_RESET | ((uint32_t)(idx >> 1) << 8))
+                           : philox(seed, env_id, episode, (uint32_t)STREAM_RESET | ((uint32_t)(idx >> 1) << 8));
     double u = (idx & 1) ? u53(r.z, r.w) : u53(r.x, r.y);
     return lo + (hi - lo) * u;
   }
@@ -751,6 +753,16 @@ void hko_reset(void* h, const uint8_t* mask, const int8_t* one_starting, float* 
   for (size_t i = 0; i < b->envs.size(); ++i) {
     if (mask && !mask[i]) continue;
     b->envs[i]->reset(one_starting ? (int)one_starting[i] : -1);
+    if (obs) b->envs[i]->getObs(obs + 18 * i);
+  }
+}
+void hko_reset_seeded(void* h, const uint8_t* mask, const int8_t* one_starting, const int64_t* seeds, float* obs) {
+  Batch* b = (Batch*)h;
+  for (size_t i = 0; i < b->envs.size(); ++i) {
+    if (mask && !mask[i]) continue;
+    b->envs[i]->reset_seed = seeds ? seeds[i] : -1;
+    b->envs[i]->reset(one_starting ? (int)one_starting[i] : -1);
+    b->envs[i]->reset_seed = -1;
     if (obs) b->envs[i]->getObs(obs + 18 * i);
   }
 }

@@ -54,6 +54,14 @@ void hs_reset(void* h, const uint8_t* mask, const int8_t* one_starting, float* o
     if (obs) getObs(b->envs[i], obs + 18 * i);
   }
 }
+void hs_reset_seeded(void* h, const uint8_t* mask, const int8_t* one_starting, const int64_t* seeds, float* obs) {
+  HostBatch* b = (HostBatch*)h;
+  for (int64_t i = 0; i < b->n; ++i) {
+    if (mask && !mask[i]) continue;
+    envReset(b->S, b->cfg, b->envs[i], (uint64_t)(b->env_id_offset + i), one_starting ? (int)one_starting[i] : -1, seeds ? seeds[i] : -1);
+    if (obs) getObs(b->envs[i], obs + 18 * i);
+  }
+}
 void hs_step(void* h, const float* action, int stride, int pol1, int pol2, int flags, float* obs, float* obs2, float* reward,
              float* reward2, uint8_t* done, float* info, float* info2, float* final_obs) {
   HostBatch* b = (HostBatch*)h;

@@ -38,6 +38,7 @@ def lib():
         L.hs_create.argtypes = [i64, i32, i32, u64, i64]
         L.hs_destroy.argtypes = [vp]
         L.hs_reset.argtypes = [vp, vp, vp, vp]
+        L.hs_reset_seeded.argtypes = [vp, vp, vp, vp, vp]
         L.hs_get_obs.argtypes = [vp, vp, vp]
         L.hs_step.argtypes = [vp, vp, i32, i32, i32, i32] + [vp] * 8
         L.hs_get_state.argtypes = [vp, vp]
@@ -72,11 +73,12 @@ class HostSimBatch:
         except Exception:
             pass
 
-    def reset(self, mask=None, one_starting=None):
+    def reset(self, mask=None, one_starting=None, seeds=None):
         obs = np.zeros((self.n, 18), np.float32)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         o = None if one_starting is None else np.ascontiguousarray(one_starting, np.int8)
-        self.L.hs_reset(self.h, _p(m), _p(o), _p(obs))
+        sd = None if seeds is None else np.ascontiguousarray(seeds, np.int64)
+        self.L.hs_reset_seeded(self.h, _p(m), _p(o), _p(sd), _p(obs))
         return obs
 
     def get_obs(self):

@@ -46,6 +46,7 @@ def lib():
         L.hko_destroy.argtypes = [vp]
         L.hko_set_modes.argtypes = [i32, i32]
         L.hko_reset.argtypes = [vp, vp, vp, vp]
+        L.hko_reset_seeded.argtypes = [vp, vp, vp, vp, vp]
         L.hko_reset_with_draws.argtypes = [vp, i64, i32, vp]
         L.hko_get_obs.argtypes = [vp, vp, vp]
         L.hko_step.argtypes = [vp, vp, i32, i32, i32, i32] + [vp] * 8
@@ -84,11 +85,12 @@ class OracleBatch:
         except Exception:
             pass
 
-    def reset(self, mask=None, one_starting=None):
+    def reset(self, mask=None, one_starting=None, seeds=None):
         obs = np.zeros((self.n, OBS_DIM), np.float32)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         o = None if one_starting is None else np.ascontiguousarray(one_starting, np.int8)
-        self.L.hko_reset(self.h, _p(m), _p(o), _p(obs))
+        sd = None if seeds is None else np.ascontiguousarray(seeds, np.int64)
+        self.L.hko_reset_seeded(self.h, _p(m), _p(o), _p(sd), _p(obs))
         return obs
 
     def reset_with_draws(self, index, draws, one_starting=-1):

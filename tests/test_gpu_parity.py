@@ -115,6 +115,112 @@ def test_state_roundtrip_and_injection(oracle):
     assert len(state_mismatches(ora.get_state(), _state(env))) == 0
 
 
+def test_set_obs_state_parity(oracle):
+    """HockeyEnv.set_state (hockey_env.py:594-608) through hk_set_obs_state: 18 visible values injected mid-game into
+    both engines (hidden state -- contacts, warm-start impulses, sleep timers, fat AABBs -- stays whatever it was, as in
+    the reference), then the same evolution."""
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    n = 512
+    env, ora = _mk(hk, O, n, 0, 41, O.POL_STRONG, O.POL_WEAK)
+    donor = O.OracleBatch(n, mode=0, seed=977, n_threads=8)  # a different game supplies reachable visible states
+    for t in range(70):
+        env.step()
+        ora.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+        donor.step(None, O.POL_WEAK, O.POL_STRONG, O.STEP_AUTORESET)
+    for rnd in range(3):
+        for _ in range(23):
+            donor.step(None, O.POL_WEAK, O.POL_STRONG, O.STEP_AUTORESET)
+        vis = donor.get_obs()[0]                       # float32-exact values
+        vis[::7, 16] = 5.0                             # some envs are handed the puck (keep_mode timers are injected too)
+        vis[3::7, 17] = 2.0
+        env.set_state(torch.from_numpy(vis).cuda())
+        ora.set_obs_state(vis.astype(np.float64))
+        bad = state_mismatches(ora.get_state(), _state(env))
+        assert len(bad) == 0, f"state differs right after set_state (round {rnd}): {bad[:8].tolist()}"
+        assert np.array_equal(env.current_obs().cpu().numpy(), ora.get_obs()[0])
+        for t in range(45):
+            env.step()
+            ro = ora.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+            _compare_step(env, ro, t)
+        bad = state_mismatches(ora.get_state(), _state(env))
+        assert len(bad) == 0, f"state differs 45 ticks after set_state (round {rnd}): {bad[:8].tolist()}"
+
+
+def test_masked_reset_with_forced_sides_parity(oracle):
+    """hk_reset(mask, one_starting) mid-episode (HockeyEnv.reset(one_starting=...), hockey_env.py:345-362): only the
+    masked envs restart, with a forced side (1/0) or the reference's alternation (-1); the others keep playing."""
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    n = 512
+    rng = np.random.default_rng(3)
+    for mode in (0, 1, 2):
+        env, ora = _mk(hk, O, n, mode, 300 + mode, O.POL_STRONG, O.POL_STRONG)
+        for rnd in range(4):
+            for t in range(37):
+                env.step()
+                ro = ora.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+                _compare_step(env, ro, t)
+            mask = rng.random(n) < 0.4
+            side = rng.integers(-1, 2, n).astype(np.int8)
+            if rnd == 3:  # reset(): everybody, alternating
+                obs, info = env.reset()
+                o_obs = ora.reset()
+            else:
+                obs, info = env.reset(mask=torch.from_numpy(mask).cuda(), one_starting=torch.from_numpy(side).cuda())
+                o_obs = ora.reset(mask=mask.astype(np.uint8), one_starting=side)
+            sel = np.ones(n, bool) if rnd == 3 else mask
+            assert np.array_equal(obs.cpu().numpy()[sel], o_obs[sel])
+            bad = state_mismatches(ora.get_state(), _state(env))
+            assert len(bad) == 0, f"mode {mode} round {rnd}: state differs after the masked reset: {bad[:8].tolist()}"
+            if mode == 0 and rnd < 3:  # forced sides took effect: the puck starts in the chosen half
+                px = obs.cpu().numpy()[:, 12]
+                assert (px[mask & (side == 1)] < 0).all() and (px[mask & (side == 0)] > 0).all()
+        for t in range(30):
+            env.step()
+            ro = ora.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+            _compare_step(env, ro, t)
+        assert len(state_mismatches(ora.get_state(), _state(env))) == 0
+    with pytest.raises(ValueError):
+        env.reset(mask=torch.ones(n - 1, dtype=torch.bool, device="cuda:0"))
+    with pytest.raises(ValueError):
+        env.reset(one_starting=torch.ones(3, dtype=torch.int8, device="cuda:0"))
+    env.reset(one_starting=np.bool_(True))  # numpy scalars take the scalar path
+
+
+@pytest.mark.parametrize("mode,p1,p2", [(0, 2, 1), (0, 0, 0), (2, 2, 4)])
+def test_keep_mode_false_parity(oracle, mode, p1, p2):
+    """HockeyEnv(keep_mode=False) (hockey_env.py:91,144-148,383-386): no keep/shoot logic, the has_puck timers never
+    start, the shoot column of the action is ignored, BasicOpponent never shoots."""
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    n = 256
+    names = {O.POL_EXTERNAL: None, O.POL_WEAK: "weak", O.POL_STRONG: "strong", O.POL_ZERO: "zero"}
+    env = hk.HockeyVecEnv(n, mode=hk.Mode(mode), keep_mode=False, device="cuda:0", seed=88, p1=names[p1], p2=names[p2],
+                          want_agent_two=True)
+    ora = O.OracleBatch(n, mode=mode, keep_mode=False, seed=88, n_threads=8)
+    assert len(state_mismatches(ora.get_state(), _state(env))) == 0
+    rng = np.random.default_rng(5)
+    for t in range(300):
+        a = None
+        if p1 == O.POL_EXTERNAL:
+            a = rng.uniform(-1.2, 1.2, (n, 8)).astype(np.float32)
+            a[:, 3] = a[:, 7] = 1.0  # "shoot" must be ignored
+            env.step(torch.from_numpy(a).cuda())
+        else:
+            env.step()
+        ro = ora.step(a, p1, p2, O.STEP_AUTORESET)
+        _compare_step(env, ro, t)
+        if t % 50 == 49:
+            assert len(state_mismatches(ora.get_state(), _state(env))) == 0, f"state differs at tick {t}"
+    assert (env.obs[:, 16:18] == 0).all()
+    s = env.stats()
+    assert s["episodes"] > 0 and s["touches_p1"] == 0 and s["touches_p2"] == 0
+
+
 def test_rollout_equals_steps(oracle):
     """hk_rollout(k) == k x hk_step with the same in-kernel policies."""
     import hockey_env_b200 as hk

@@ -101,3 +101,106 @@ def test_shard_invariance(oracle, hostsim):
     sf = full.get_state()
     assert np.array_equal(sf[:32], a.get_state()) and np.array_equal(sf[32:], b.get_state())
     assert np.allclose(full.stats()[:5], a.stats()[:5] + b.stats()[:5])
+
+
+def test_set_obs_state_mid_game(oracle, hostsim):
+    """set_state on envs that are in the middle of a game (live contacts, warm-start impulses, has_puck timers)."""
+    O, H = oracle, hostsim
+    n = 96
+    o = O.OracleBatch(n, mode=0, seed=41)
+    h = H.HostSimBatch(n, mode=0, seed=41, fast=True)
+    donor = O.OracleBatch(n, mode=0, seed=977)
+    for _ in range(70):
+        o.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+        h.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+        donor.step(None, O.POL_WEAK, O.POL_STRONG, O.STEP_AUTORESET)
+    for rnd in range(3):
+        for _ in range(23):
+            donor.step(None, O.POL_WEAK, O.POL_STRONG, O.STEP_AUTORESET)
+        vis = donor.get_obs()[0]
+        vis[::7, 16] = 5.0
+        vis[3::7, 17] = 2.0
+        o.set_obs_state(vis.astype(np.float64))
+        h.set_obs_state(vis)
+        assert len(state_mismatches(o.get_state(), h.get_state())) == 0, rnd
+        for t in range(45):
+            ra = o.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+            rb = h.step(None, O.POL_STRONG, O.POL_WEAK, O.STEP_AUTORESET)
+            assert outputs_equal(ra, rb) == [], (rnd, t)
+        assert len(state_mismatches(o.get_state(), h.get_state())) == 0, rnd
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_masked_reset_with_forced_sides(oracle, hostsim, mode):
+    """reset(mask, one_starting) mid-episode (hockey_env.py:345-362): forced side 1/0 or alternation (-1)."""
+    O, H = oracle, hostsim
+    n = 96
+    rng = np.random.default_rng(3 + mode)
+    o = O.OracleBatch(n, mode=mode, seed=300 + mode)
+    h = H.HostSimBatch(n, mode=mode, seed=300 + mode, fast=True)
+    for rnd in range(4):
+        for t in range(37):
+            ra = o.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+            rb = h.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+            assert outputs_equal(ra, rb) == [], (rnd, t)
+        if rnd == 3:
+            oa, ob = o.reset(), h.reset()
+            sel = np.ones(n, bool)
+        else:
+            mask = (rng.random(n) < 0.4).astype(np.uint8)
+            side = rng.integers(-1, 2, n).astype(np.int8)
+            oa, ob = o.reset(mask=mask, one_starting=side), h.reset(mask=mask, one_starting=side)
+            sel = mask.astype(bool)
+            if mode == 0:
+                assert (oa[sel & (side == 1), 12] < 0).all() and (oa[sel & (side == 0), 12] > 0).all()
+        assert np.array_equal(oa[sel], ob[sel])
+        assert len(state_mismatches(o.get_state(), h.get_state())) == 0, rnd
+
+
+@pytest.mark.parametrize("mode,p1,p2", [(0, 2, 1), (0, 0, 0), (2, 2, 4)])
+def test_keep_mode_false(oracle, hostsim, mode, p1, p2):
+    """keep_mode=False (hockey_env.py:91,144-148): no keep/shoot, timers never start, shoot column ignored."""
+    O, H = oracle, hostsim
+    n = 64
+    o = O.OracleBatch(n, mode=mode, keep_mode=False, seed=88)
+    h = H.HostSimBatch(n, mode=mode, keep_mode=False, seed=88, fast=True)
+    rng = np.random.default_rng(5)
+    for t in range(300):
+        a = None
+        if p1 == O.POL_EXTERNAL:
+            a = rng.uniform(-1.2, 1.2, (n, 8)).astype(np.float32)
+            a[:, 3] = a[:, 7] = 1.0
+        ra = o.step(a, p1, p2, O.STEP_AUTORESET)
+        rb = h.step(a, p1, p2, O.STEP_AUTORESET)
+        assert outputs_equal(ra, rb) == [], t
+        assert (ra["obs"][:, 16:18] == 0).all()
+    assert len(state_mismatches(o.get_state(), h.get_state())) == 0
+    assert o.stats()[0] == h.stats()[0] > 0
+
+
+def test_seeded_reset(oracle, hostsim):
+    """reset(seed=s) (hockey_env.py:347: the reference reseeds on every reset): the start state is a function of the
+    seed alone -- same seed, same draws, on any env of any batch; unseeded envs continue their own stream."""
+    O, H = oracle, hostsim
+    n = 64
+    for mode in (0, 1, 2):
+        o = O.OracleBatch(n, mode=mode, seed=7)
+        h = H.HostSimBatch(n, mode=mode, seed=7, fast=True)
+        o2 = O.OracleBatch(n, mode=mode, seed=12345, env_id_offset=999)  # another batch, other library seed
+        for _ in range(20):
+            o.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+            h.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+        seeds = np.arange(n, dtype=np.int64) % 8 + 100
+        seeds[1::4] = -1
+        side = np.ones(n, np.int8)
+        a, b = o.reset(one_starting=side, seeds=seeds), h.reset(one_starting=side, seeds=seeds)
+        c = o2.reset(one_starting=side, seeds=seeds)
+        assert np.array_equal(a, b)
+        assert len(state_mismatches(o.get_state(), h.get_state())) == 0
+        sel = seeds >= 0
+        assert np.array_equal(a[sel, :16], c[sel, :16])             # independent of batch, env id and library seed (the
+                                                                    # has_puck timers are not reset by the reference)
+        assert np.array_equal(a[0, :16], a[8, :16]) and np.array_equal(a[2, :16], a[10, :16])   # same seed -> same start
+        if mode != 0:
+            assert not np.array_equal(a[0, :16], a[2, :16])         # different seeds differ
+        assert not np.array_equal(a[~sel][:4, :16], c[~sel][:4, :16])   # unseeded envs keep their own streams

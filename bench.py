@@ -1,17 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/sec of the batched HockeyEnv hot path (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle restatement) on the host cores
+  python bench.py --gpus N --steps K --warmup W [--config NAME]   # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...         # the CPU path (oracle restatement) on the host cores
 
-A "step" is one tick of every env of the batch (one hk_step call per GPU = the kernel cascade k_fast -> k_general):
-physics, contact sensing,
-rewards, observation write, in-kernel BasicOpponents and auto-reset.  Workload (config.workload): 65,536
-NORMAL-mode envs per GPU, strong-vs-strong BasicOpponent (weak scaling: envs are independent, sharded by
-contiguous global env ids, no per-step communication; episode statistics are all-reduced once at the end).
+A "step" is one tick of every env of the batch (one hk_step call per GPU): physics, contact sensing, rewards,
+observation write, in-kernel opponents and auto-reset.  Workloads (`--config`, BASELINE.json `configs`):
 
-Timing: W untimed warm-up steps, then K steps each bracketed by CUDA events on the launching stream with an L2
-flush (256 MiB memset, untimed) between steps, barrier + synchronize on both sides, MAX over ranks.
+  normal65k   (default) 65,536 NORMAL envs per GPU, strong-vs-strong in-kernel BasicOpponent  -- the headline metric
+  shooting4k  4,096 TRAIN_SHOOTING envs per GPU, U(-1,1) random actions for both players      -- configs[1]
+  defense65k  65,536 TRAIN_DEFENSE envs per GPU, strong BasicOpponent vs zero action          -- configs[2]
+  defense65k_weak  same with a weak BasicOpponent as player 2
+  normal1M    1,048,576 NORMAL envs IN TOTAL (sharded over the GPUs), strong vs strong        -- configs[3], north_star target
+  actor262k   262,144 NORMAL envs in total, player 1 = the reference's trained TD3 actor (stage_3 weights, torch
+              matmuls on the obs tensor in place), player 2 = in-kernel strong BasicOpponent  -- configs[4]
+
+Envs are independent: contiguous global-env-id shards, no per-step communication; episode statistics are all-reduced
+once at the end (NCCL).
+
+Steady state: episodes start synchronised after a reset, and the first ticks (no puck has reached a wall or a racket
+yet) are far cheaper than the stationary mix.  Both arms therefore run an UNTIMED pre-roll of >= 400 ticks first,
+independent of --warmup, extended until the TOI-event rate of two consecutive 100-tick windows agrees within 20 %.
+Timing: W untimed warm-up steps through the timed call path, then K steps each bracketed by CUDA events on the launching
+stream with an L2 flush (256 MiB memset, untimed) between steps, barrier + synchronize on both sides, MAX over ranks.
 """
 import argparse
 import json
@@ -23,17 +34,50 @@ import time
 _ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, _ROOT)
 
-ENVS_PER_GPU = 65536
-# algorithmic bytes per env-step of the dominant kernel (DESIGN.md "Data layout"): 256 B state read + 256 B state
-# written + obs 72 + reward 4 + done 1 + info 16 (in-kernel opponents: no action read)
-ALGO_BYTES_PER_ENV_STEP = 256 + 256 + 72 + 4 + 1 + 16
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel (k_general<1>) for one launch at 65,536 envs, from the
-# `ncu --set full` capture summarised in profiles/r1e_raw_metrics.csv (44.3 MB read + 33.8 MB written)
-NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 = 78_094_592
-# smsp__inst_executed.sum of one tick at 65,536 envs from the same capture (k_fast 22.4 M + k_general 51.6 M warp
-# instructions) and the issue ceiling of SURVEY.md section 8(d): 148 SMs x 4 schedulers x 1 warp-inst/clk x 1.965 GHz
-NCU_WARP_INST_PER_TICK_65536 = 22_403_347 + 51_615_094
-ISSUE_PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9
+# algorithmic bytes per env-step (96 B state record read + written, obs 72, reward 4, done 1,
+# info 16; + 32 B action read when actions are external).  STORED_* is what this implementation actually keeps per env
+# in HBM (256 B core record incl. fat AABBs, contact list, RNG counters, episode returns) -- reported beside it.
+ALGO_BYTES_FUSED, ALGO_BYTES_EXTERNAL = 285, 317
+STORED_BYTES_FUSED = 256 + 256 + 72 + 4 + 1 + 16
+ISSUE_PEAK_WARP_INST_PER_S = 148 * 4 * 1.965e9  # 148 SMs x 4 schedulers x 1 warp-inst/clk x 1.965 GHz
+PREROLL_TICKS = 400
+
+CONFIGS = {
+    "normal65k": dict(mode="NORMAL", p1="strong", p2="strong", per_gpu=65536, total=None,
+                      text="65536 NORMAL envs per GPU, strong-vs-strong in-kernel BasicOpponent"),
+    "shooting4k": dict(mode="TRAIN_SHOOTING", p1="random", p2="random", per_gpu=4096, total=None,
+                       text="4096 TRAIN_SHOOTING envs per GPU, U(-1,1) random actions for both players"),
+    "defense65k": dict(mode="TRAIN_DEFENSE", p1="strong", p2="zero", per_gpu=65536, total=None,
+                       text="65536 TRAIN_DEFENSE envs per GPU, strong BasicOpponent vs zero action"),
+    "defense65k_weak": dict(mode="TRAIN_DEFENSE", p1="strong", p2="weak", per_gpu=65536, total=None,
+                            text="65536 TRAIN_DEFENSE envs per GPU, strong vs weak BasicOpponent"),
+    "normal1M": dict(mode="NORMAL", p1="strong", p2="strong", per_gpu=None, total=1048576,
+                     text="1048576 NORMAL envs in total, strong-vs-strong in-kernel BasicOpponent"),
+    "actor262k": dict(mode="NORMAL", p1="actor", p2="strong", per_gpu=None, total=262144,
+                      text="262144 NORMAL envs in total, player 1 = TD3 actor (stage_3 weights, on device), player 2 = "
+                           "in-kernel strong BasicOpponent"),
+}
+
+
+def resolve(args, world):
+    c = dict(CONFIGS[args.config])
+    if args.envs:
+        n, scaling = args.envs, "weak"
+    elif c["total"]:
+        n, scaling = c["total"] // world, "strong"
+    else:
+        n, scaling = c["per_gpu"], "weak"
+    c["n"], c["scaling"] = n, scaling
+    return c
+
+
+def config_dict(args, c, world):
+    """Identical for both arms (the driver compares them)."""
+    return {"workload": f"{args.config}: {c['text']}, auto-reset, all per-tick outputs (obs/reward/done/info) written",
+            "name": args.config, "envs_per_gpu": c["n"], "mode": c["mode"], "p1": c["p1"], "p2": c["p2"],
+            "parallelism": f"env-sharded x{world}, no per-step communication",
+            "steady_state": f">= {PREROLL_TICKS} untimed pre-roll ticks before warm-up",
+            "l2": "no flush" if args.no_l2_flush else "flushed between timed steps (256 MiB memset, untimed)"}
 
 
 def _peaks():
@@ -43,6 +87,15 @@ def _peaks():
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _capture(name):
+    """ncu numbers of the dominant kernel for this workload, extracted from the committed capture of this build
+    (scripts/extract_profiles.py -> profiles/roofline_capture.json); None if there is no capture for it."""
+    try:
+        return json.load(open(os.path.join(_ROOT, "profiles", "roofline_capture.json"))).get(name)
+    except Exception:
+        return None
 
 
 class ClockSampler(threading.Thread):
@@ -93,67 +146,99 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+# ---- CPU legs (the oracle restatement; the one place outside tests/ and smoke() that executes oracle/) -------------------
+def _oracle_batch(c, n, seed, cores):
+    sys.path.insert(0, os.path.join(_ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as O
+    mode = {"NORMAL": O.MODE_NORMAL, "TRAIN_SHOOTING": O.MODE_TRAIN_SHOOTING, "TRAIN_DEFENSE": O.MODE_TRAIN_DEFENSE}[c["mode"]]
+    pol = {"strong": O.POL_STRONG, "weak": O.POL_WEAK, "random": O.POL_RANDOM, "zero": O.POL_ZERO,
+           "actor": O.POL_STRONG}  # CPU legs: the actor's GEMMs are not part of the env path; a strong BasicOpponent stands in
+    b = O.OracleBatch(n, mode=mode, seed=seed, n_threads=cores)
+    b.reset(one_starting=(np.arange(n) % 2).astype(np.int8))
+    return b, pol[c["p1"]], pol[c["p2"]]
+
+
+def _oracle_preroll(b, p1, p2):
+    """Pre-roll to the stationary episode-phase mix; returns TOI events per env-step of the last 100-tick window."""
+    b.rollout(PREROLL_TICKS - 200, p1, p2)
+    rate = []
+    for _ in range(12):
+        b.clear_stats()
+        b.rollout(100, p1, p2)
+        s = b.stats()
+        rate.append(s[12] / max(s[4], 1))
+        if len(rate) >= 2 and abs(rate[-1] - rate[-2]) <= 0.2 * max(rate[-2], 1e-9):
+            break
+    b.clear_stats()
+    return rate[-1]
+
+
 def run_reference(args, rank, world):
-    """The reference arm for this tier: the CPU implementation of the path (the oracle restatement of
-    hockey_env.py + Box2D step; the reference's own pybox2d build is not installable here) on all host threads."""
+    """Reference arm for this tier: the CPU implementation of the path (the oracle restatement of hockey_env.py + the
+    Box2D step; the reference's own pybox2d build is not installable here) on all host threads, same
+    workload; one step = one tick of a bounded sample of the batch, advanced in rollout chunks."""
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(_ROOT, "tests"))
-    import oracle_lib as O
+    c = resolve(args, world)
     cores = os.cpu_count() or 1
-    n = 1024 * cores  # bounded sample of the 65,536-env workload (large enough to amortise the per-tick thread start)
-    b = O.OracleBatch(n, mode=O.MODE_NORMAL, seed=args.seed, n_threads=cores)
-    import numpy as np
-    b.reset(one_starting=(np.arange(n) % 2).astype(np.int8))
-    for _ in range(args.warmup):
-        b.rollout(1, O.POL_STRONG, O.POL_STRONG)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        b.rollout(1, O.POL_STRONG, O.POL_STRONG)
+    n = min(c["n"], 2048 * cores)
+    b, p1, p2 = _oracle_batch(c, n, args.seed, cores)
+    toi_tail = _oracle_preroll(b, p1, p2)
+    chunk = 5
+    for _ in range((args.warmup + chunk - 1) // chunk):
+        b.rollout(chunk, p1, p2)
+    b.clear_stats()
+    done, t0 = 0, time.perf_counter()
+    while done < args.steps:
+        k = min(chunk, args.steps - done)
+        b.rollout(k, p1, p2)
+        done += k
     dt = time.perf_counter() - t0
+    s = b.stats()
     value = n * args.steps / dt
-    sample = f"{n} NORMAL envs x {args.steps} ticks, strong-vs-strong BasicOpponent, {cores} threads"
+    sample = f"{n} of {c['n']} envs x {args.steps} ticks in rollout chunks of {chunk}, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "65536 NORMAL envs/GPU, strong-vs-strong BasicOpponent, auto-reset (bounded CPU sample)",
-                   "sample_envs": n},
+        "scaling": c["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(args, c, world),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "episode_stats": {"episodes": s[0], "env_steps": s[4], "toi_events_per_step": s[12] / max(s[4], 1),
+                          "toi_events_per_step_preroll_tail": toi_tail},
     }), flush=True)
 
 
-def cpu_baseline(seed, budget_s=12.0):
-    """Oracle ("port") timed on the host cores on a bounded sample of the same workload."""
-    sys.path.insert(0, os.path.join(_ROOT, "tests"))
-    import numpy as np
-    import oracle_lib as O
+def cpu_baseline(args, c, budget_s=12.0):
+    """Oracle ("port") timed on the host cores on a bounded sample of the same workload, in steady state."""
     cores = os.cpu_count() or 1
-    n = 128 * cores
-    b = O.OracleBatch(n, mode=O.MODE_NORMAL, seed=seed, n_threads=cores)
-    b.reset(one_starting=(np.arange(n) % 2).astype(np.int8))
-    b.rollout(20, O.POL_STRONG, O.POL_STRONG)
+    n = min(c["n"], 256 * cores)
+    b, p1, p2 = _oracle_batch(c, n, args.seed, cores)
+    _oracle_preroll(b, p1, p2)
     steps, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s:
-        b.rollout(50, O.POL_STRONG, O.POL_STRONG)
-        steps += 50
+        b.rollout(25, p1, p2)
+        steps += 25
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n} NORMAL envs x {steps} ticks, strong-vs-strong BasicOpponent, {cores} threads, {dt:.1f} s"}
+            "sample": f"{n} of {c['n']} envs x {steps} ticks after a {PREROLL_TICKS}+ tick pre-roll, {cores} threads, {dt:.1f} s"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
+    ap.add_argument("--config", default="normal65k", choices=sorted(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (overrides the config's size)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--rollout-k", type=int, default=64, help="ticks per hk_rollout call of the fused-rollout leg (0 = skip)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -175,10 +260,31 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n = args.envs
-    env = hk.HockeyVecEnv(n, mode=hk.Mode.NORMAL, device=dev, seed=args.seed, env_id_offset=rank * n, p1="strong", p2="strong")
+    c = resolve(args, world)
+    n = c["n"]
+    mode = hk.Mode[c["mode"]]
+    actor = None
+    if c["p1"] == "actor":
+        actor = hk.load_td3_actor(os.path.join(_ROOT, "tests", "golden", "td3_actors.npz"), device=dev, name="stage_3")
+    env = hk.HockeyVecEnv(n, mode=mode, device=dev, seed=args.seed, env_id_offset=rank * n,
+                          p1=None if actor is not None else c["p1"], p2=c["p2"])
     env.reset(one_starting=(torch.arange(n, device=dev) % 2).to(torch.int8))
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev_actor = []
+
+    def tick(timed=False):
+        if actor is None:
+            env.step()
+            return
+        with torch.no_grad():
+            if timed:
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+            a = actor(env.obs)
+            if timed:
+                a1.record()
+                ev_actor.append((a0, a1))
+            env.step(a)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -186,9 +292,29 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- untimed pre-roll to the stationary episode-phase mix --------------------------------------------------------------
+    def advance(k):
+        if actor is None:
+            env.rollout(k, c["p1"], c["p2"])
+        else:
+            for _ in range(k):
+                tick()
+
+    advance(PREROLL_TICKS - 200)
+    rates = []
+    for _ in range(12):
+        env.clear_stats()
+        advance(100)
+        s = env.stats()
+        rates.append(s["toi_events"] / max(s["env_steps"], 1))
+        if len(rates) >= 2 and abs(rates[-1] - rates[-2]) <= 0.2 * max(rates[-2], 1e-9):
+            break
+    preroll_ticks = PREROLL_TICKS - 200 + 100 * len(rates)
+
     for _ in range(args.warmup):
-        env.step()
+        tick()
     env.clear_stats()
+    env.kernel_timing(True)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -197,92 +323,137 @@ def main():
         if flush is not None:
             flush.zero_()
         ev[k][0].record()
-        env.step()
+        tick(timed=True)
         ev[k][1].record()
     barrier()
     clocks = sampler.stop()
     kernel_ms = sum(a.elapsed_time(b) for a, b in ev)
+    actor_ms = sum(a.elapsed_time(b) for a, b in ev_actor)
+    ktimes, ksteps = env.kernel_times()
+    env.kernel_timing(False)
     t = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     kernel_ms = float(t.item())
     value = world * n * args.steps / (kernel_ms * 1e-3)
+    st = env.stats_tensor()
+
+    # ---- fused rollout (hk_rollout): K ticks per call, no per-tick outputs -- reported beside the headline, never as it ----
+    rollout = None
+    if args.rollout_k > 0 and actor is None:
+        calls = max(2, min(8, (args.steps + args.rollout_k - 1) // args.rollout_k))
+        env.rollout(args.rollout_k, c["p1"], c["p2"])
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for _ in range(calls):
+            env.rollout(args.rollout_k, c["p1"], c["p2"])
+        r1.record()
+        barrier()
+        t = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rollout = {"value": world * n * calls * args.rollout_k / (float(t.item()) * 1e-3), "unit": "env-steps/s",
+                   "k_steps": args.rollout_k, "calls": calls,
+                   "note": "hk_rollout: in-kernel policies, auto-reset, statistics only (no per-tick outputs, no L2 flush)"}
 
     # ---- end to end through the public API with HOST buffers: player-1 actions come from pinned host memory every
     # tick, obs/reward/done/info go back to pinned host memory every tick (what a host-side agent would do).
-    e2e_env = hk.HockeyVecEnv(n, mode=hk.Mode.NORMAL, device=dev, seed=args.seed + 1, env_id_offset=rank * n, p2="strong")
-    h_act = torch.empty((n, 4), dtype=torch.float32).uniform_(-1, 1).pin_memory()
-    d_act = torch.empty((n, 4), dtype=torch.float32, device=dev)
-    h_obs = torch.empty((n, 18), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
-    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    h_info = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    e2e = None
+    if not args.no_e2e:
+        p2 = c["p2"]
+        e2e_env = hk.HockeyVecEnv(n, mode=mode, device=dev, seed=args.seed + 1, env_id_offset=rank * n, p2=p2)
+        e2e_env.reset(one_starting=(torch.arange(n, device=dev) % 2).to(torch.int8))
+        h_act = torch.empty((n, 4), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+        host = e2e_env.host_buffers()
 
-    def e2e_tick():
-        d_act.copy_(h_act, non_blocking=True)
-        obs, rew, done, _, _ = e2e_env.step(d_act)
-        h_obs.copy_(obs, non_blocking=True)
-        h_rew.copy_(rew, non_blocking=True)
-        h_done.copy_(done, non_blocking=True)
-        h_info.copy_(e2e_env.info, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()  # the host needs the results before it can pick the next action
+        def e2e_tick():
+            e2e_env.step_host(h_act, host)  # H2D actions, tick, D2H packed outputs, stream sync
 
-    for _ in range(max(3, args.warmup // 10)):
-        e2e_tick()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.e2e_steps):
-        e2e_tick()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.e2e_steps / (float(t.item()) * 1e-3)
+        for _ in range(PREROLL_TICKS):
+            e2e_env.step_host(h_act, host, sync=False)
+        for _ in range(max(3, args.warmup)):
+            e2e_tick()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.e2e_steps):
+            e2e_tick()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * args.e2e_steps / (float(t.item()) * 1e-3), "unit": "env-steps/s",
+               "h2d_bytes_per_step": h_act.numel() * 4, "d2h_bytes_per_step": e2e_env.host_bytes_per_step(),
+               "steps": args.e2e_steps,
+               "note": "HockeyVecEnv.step_host: player-1 actions from pinned host memory, obs/reward/done/info packed "
+                       f"to pinned host memory, host sync every tick; player 2 = in-kernel {p2}; after a "
+                       f"{PREROLL_TICKS}-tick pre-roll"}
+        e2e_env.close()
 
     # ---- end-of-run statistics: the only collective on this path (NCCL all-reduce of 16 doubles)
-    st = env.stats_tensor()
     if world > 1:
         dist.all_reduce(st, op=dist.ReduceOp.SUM)
     st = st.cpu().tolist()
 
     if rank == 0:
         peak, peak_src = _peaks()
-        bytes_per_launch = ALGO_BYTES_PER_ENV_STEP * n
-        achieved = bytes_per_launch / (kernel_ms / args.steps * 1e-3) / 1e9
+        ms_tick = kernel_ms / args.steps
+        algo = ALGO_BYTES_EXTERNAL if actor is not None else ALGO_BYTES_FUSED
+        # dominant kernel = the one with the largest summed device time in the timed region (events on the launching stream)
+        dom = max(ktimes, key=lambda k: ktimes[k])
+        dom_ms = ktimes[dom] / max(ksteps, 1)
+        # units one launch of it processes: all envs for k_fast, the queued envs for the general tier
+        gen_units = st[14] / max(args.steps * world, 1)
+        units = float(n) if dom == "k_fast" else gen_units
+        achieved = algo * units / (dom_ms * 1e-3) / 1e9
+        cap = _capture(args.config)
+        issue = None
+        if cap and cap.get("warp_inst_per_tick"):
+            issue = {"achieved": cap["warp_inst_per_tick"] / (ms_tick * 1e-3), "peak": ISSUE_PEAK_WARP_INST_PER_S, "unit": "warp-inst/s",
+                     "frac": cap["warp_inst_per_tick"] / (ms_tick * 1e-3) / ISSUE_PEAK_WARP_INST_PER_S,
+                     "capture_frac": cap["warp_inst_per_tick"] / (cap["capture_ms_per_tick"] * 1e-3) / ISSUE_PEAK_WARP_INST_PER_S
+                     if cap.get("capture_ms_per_tick") else None,
+                     "note": f"warp instructions per tick from the steady-state ncu capture of this build ({cap.get('source')}), "
+                             "divided by the tick time measured in this run; capture_frac uses the capture run's own tick time"}
         out = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": kernel_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_tick, "higher_is_better": True, "scaling": c["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{n} NORMAL envs per GPU, strong-vs-strong in-kernel BasicOpponent, auto-reset, all "
-                                   "per-tick outputs (obs/reward/done/info) written", "envs_per_gpu": n,
-                       "parallelism": f"env-sharded x{world}, no per-step communication",
-                       "l2": "no flush" if flush is None else "flushed between timed steps (256 MiB memset, untimed)"},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16,
-                    "d2h_bytes_per_step": n * (72 + 4 + 1 + 16), "steps": args.e2e_steps,
-                    "note": "player-1 actions from pinned host memory, obs/reward/done/info to pinned host memory, "
-                            "host sync every tick; player 2 = in-kernel strong BasicOpponent"},
-            # kernels of this repo launched in the timed region: k_fast, k_touch and the general tier(s) per tick
+            "config": config_dict(args, c, world),
+            "e2e": e2e,
+            "rollout": rollout,
+            # kernels of this repo launched in the timed region: k_fast (+ k_touch) + the general tier(s) per tick
             "gpu_launches": args.steps * env.launches_per_step(),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH_65536 if n == 65536 else None,
-                         "traffic_unit": "bytes per launch of the dominant kernel k_general<1> (ncu, profiles/)",
-                         "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
-                         "issue": None if n != 65536 else {
-                             "achieved": NCU_WARP_INST_PER_TICK_65536 / (kernel_ms / args.steps * 1e-3), "peak": ISSUE_PEAK_WARP_INST_PER_S,
-                             "unit": "warp-inst/s", "frac": NCU_WARP_INST_PER_TICK_65536 / (kernel_ms / args.steps * 1e-3) / ISSUE_PEAK_WARP_INST_PER_S,
-                             "note": "warp instructions per tick from ncu (profiles/r1e_raw_metrics.csv) / measured tick time"},
-                         "note": "achieved = algorithmic bytes of one tick (all kernels of the cascade) / tick time; the path "
-                                 "is instruction-fetch/divergence bound, not HBM-bound (DESIGN.md section 4, profiles/README.md)"},
+            "kernel_ms_per_tick": {k: v / max(ksteps, 1) for k, v in ktimes.items()},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": cap.get("dram_bytes_per_launch") if cap else None,
+                         "traffic_unit": "dram bytes per launch of the dominant kernel (ncu --set full capture of this build, profiles/)",
+                         "algorithmic_bytes_per_env_step": algo, "units_per_launch": units,
+                         "algorithmic_bytes_per_launch": algo * units, "kernel_ms_per_launch": dom_ms,
+                         "stored_bytes_per_env_step": STORED_BYTES_FUSED + (32 if actor is not None else 0),
+                         "whole_tick": {"achieved": algo * n / (ms_tick * 1e-3) / 1e9, "frac": algo * n / (ms_tick * 1e-3) / 1e9 / peak,
+                                        "note": "all kernels of the tick, all envs"},
+                         "peak_source": peak_src, "issue": issue,
+                         "note": "achieved = SURVEY 8(d) algorithmic bytes x env-steps one launch of the dominant kernel completes / "
+                                 "its mean launch duration (CUDA events on the launching stream, this run); the path is "
+                                 "latency/issue bound, not HBM-bound (DESIGN.md section 4)"},
             "episode_stats": {"episodes": st[0], "wins": st[1], "losses": st[2], "draws": st[3], "env_steps": st[4],
                               "mean_len": st[8] / max(st[0], 1), "velocity_iters_per_step": st[11] / max(st[4], 1),
-                              "toi_events_per_step": st[12] / max(st[4], 1), "overflows": st[13]},
+                              "toi_events_per_step": st[12] / max(st[4], 1), "overflows": st[13],
+                              "general_tier_share": st[14] / max(st[4], 1),
+                              "toi_events_per_step_preroll_tail": rates[-1], "preroll_ticks": preroll_ticks},
         }
+        if actor is not None:
+            out["actor"] = {"ms_per_step": actor_ms / args.steps, "share_of_step": actor_ms / max(kernel_ms, 1e-9),
+                            "weights": "tests/golden/td3_actors.npz:stage_3 (pretrained/stage_3/models/td3_best.pt)",
+                            "flops_per_env": 2 * (18 * 256 + 256 * 256 + 256 * 4)}
+        if st[0] <= 0:
+            out["warning"] = "no episode finished in the timed region"
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.seed)
+            out["cpu_baseline"] = cpu_baseline(args, c)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -180,23 +180,35 @@ enum { Q_CLASSES = 4, QC_DONE1 = 4, QC_COUNT2 = 5, QC_DONE2 = 6 };
 template <int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_fast(KParams P, StepIO io) {
   __shared__ Scene S;
+  __shared__ __align__(16) float sRows[kBlock / 32][32 * 18];  // per warp: its 32 observation rows, staged for 128-bit stores
   stageScene(&S);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < P.n;
   TickStats st;
   tickStatsZero(st);
-  bool ok = false;
+  bool ok = false, wroteFinal = false;
   int cls = 0;
+  const bool stageRows = io.write != 0 && io.stageRows != 0;  // uniform
+  float* const myRows = sRows[threadIdx.x >> 5];
   if (valid) {
     Env e;
     loadEnv(P.core, P.n, i, e);
     e.bailKind = 15;
-    ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st);
-    if (ok) storeEnv(P.core, P.n, i, e);
-    else {
+    ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st, stageRows ? &wroteFinal : nullptr);
+    if (ok) {
+      storeEnv(P.core, P.n, i, e);
+      if (stageRows) getObs(e, myRows + 18 * (threadIdx.x & 31));
+    } else {
       tickStatsZero(st);
       cls = bailClass(e.bailKind);
     }
+  }
+  if (stageRows) {  // the warp's envs are consecutive: write its finished rows front to back, 16 bytes per lane
+    __syncwarp();
+    const int64_t i0 = i - (threadIdx.x & 31);
+    const unsigned okMask = __ballot_sync(0xffffffffu, ok), finMask = __ballot_sync(0xffffffffu, ok && !wroteFinal);
+    if (okMask) warpStoreRows18(io.obs + 18 * i0, myRows, okMask);
+    if (io.final_obs && finMask) warpStoreRows18(io.final_obs + 18 * i0, myRows, finMask);
   }
   const bool need = valid && !ok;
   const int lane = threadIdx.x & 31;
@@ -723,6 +735,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         if (need) P.queue[(int64_t)Q_CLASSES * P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
       }
     }
+    flushInt(P.stats, 14, st.steps, lane);  // env-ticks completed by the general tiers (units of work per launch)
     flushStats(P.stats, st);
   }
   if (P.trace && valid) {
@@ -976,6 +989,7 @@ struct hk_env {
   long long shapeKey() const { return carveout ? ((long long)device << 56) ^ ((long long)block1 << 40) ^ ((long long)classWarps1 << 44) ^ (long long)gridSlow(lanes1, envWarps1, classWarps1) : -2; }
   int fastBlock = kBlock;  // threads per block of k_fast / k_touch (HK_FAST_BLOCK: 32..128)
   size_t staticSmem = sizeof(Scene) + 2048;  // static shared memory of k_general (queried at creation)
+  size_t fastSmem = sizeof(Scene) + sizeof(float) * kBlock * 18;  // ... of k_fast
   // The carve-out preference is per-function, process-global state: it is set when a handle is created and again only
   // when the previous launch came from a handle with another shape (two handles of different batch sizes in one process).
   void shapeSharedMemory() const {
@@ -984,9 +998,17 @@ struct hk_env {
     const size_t stat = staticSmem;
     const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
     cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? 1 : perSm1)));
-    cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 4));
-    cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 5));
+    cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
+    cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
     cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 3));
+  }
+  // Per-kernel timing (hk_kernel_timing): CUDA events recorded on the launching stream around every kernel of a tick,
+  // kTimedSteps ticks deep; off by default (an event record is not part of a plain hk_step).
+  enum { kTimedSteps = 2048, kEventsPerStep = 5 };
+  cudaEvent_t* events = nullptr;
+  mutable int timedSteps = 0;
+  void stamp(int k, cudaStream_t stream) const {
+    if (events && timedSteps < kTimedSteps) cudaEventRecord(events[timedSteps * kEventsPerStep + k], stream);
   }
   void launchCascade(const StepIO& io, cudaStream_t stream) const {
     if (g_shapedFor != shapeKey()) {
@@ -994,13 +1016,19 @@ struct hk_env {
       g_shapedFor = shapeKey();
     }
     if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (20 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
+    stamp(0, stream);
     if (n < 100000) k_fast<4><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     else k_fast<5><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    stamp(1, stream);
     if (touch) k_touch<<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    stamp(2, stream);
     const int b2 = blockTier2(), w2 = b2 / 32;
     k_general<1><<<gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(
         params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
+    stamp(3, stream);
     if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), io, 1, lanes2, 0, phaseSync, w2, 0);
+    stamp(4, stream);
+    if (events && timedSteps < kTimedSteps) ++timedSteps;
   }
 };
 
@@ -1081,6 +1109,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 16) sms = 148;
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k_general<1>) == cudaSuccess) h->staticSmem = fa.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fa, k_fast<4>) == cudaSuccess) h->fastSmem = fa.sharedSizeBytes;
     h->targetBlocks = sms;  // one general-tier block per SM in a single wave (measured: 148 > 140 > 132 on a 148-SM B200)
     h->shapeTier1();
     h->launches = h->mono ? 1 : 2 + (h->touch ? 1 : 0) + (h->tiers == 3 ? 1 : 0);
@@ -1136,6 +1165,10 @@ int hk_destroy(hk_env* h) {
   cudaFree(h->phaseClk);
   cudaFree(h->actBuf);
   cudaFree(h->trace);
+  if (h->events) {
+    for (int k = 0; k < hk_env::kTimedSteps * hk_env::kEventsPerStep; ++k) cudaEventDestroy(h->events[k]);
+    delete[] h->events;
+  }
   delete h;
   return HK_OK;
 }
@@ -1163,6 +1196,9 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
   if (!validPolicy(p1_policy) || !(validPolicy(p2_policy) || perEnv)) return fail(HK_E_INVALID, "hk_step: invalid policy id");
   if (perEnv && !h->pol2v) return fail(HK_E_INVALID, "hk_step: HK_POLICY_PER_ENV without hk_set_opponent_policies");
   if (!obs_dev) return fail(HK_E_INVALID, "hk_step: obs_dev is required");
+  if ((((uintptr_t)info_dev | (uintptr_t)info2_dev) & 15u) != 0) return fail(HK_E_INVALID, "hk_step: info tensors must be 16-byte aligned");
+  if ((((uintptr_t)obs_dev | (uintptr_t)obs2_dev | (uintptr_t)final_obs_dev) & 7u) != 0)
+    return fail(HK_E_INVALID, "hk_step: observation tensors must be 8-byte aligned");
   if ((p1_policy == HK_POLICY_EXTERNAL || p2_policy == HK_POLICY_EXTERNAL) && !action_dev)
     return fail(HK_E_INVALID, "hk_step: action_dev is NULL but a policy is EXTERNAL");
   if (p1_policy == HK_POLICY_EXTERNAL && action_stride < 4) return fail(HK_E_INVALID, "hk_step: action_stride < 4");
@@ -1189,6 +1225,8 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
   io.final_obs = final_obs_dev;
   io.write = 1;
   io.actBuf = nullptr;
+  // k_fast writes a warp's 32 rows with 128-bit stores when the row tensors are 16-byte aligned (torch tensors are)
+  io.stageRows = (((uintptr_t)obs_dev | (uintptr_t)final_obs_dev) & 15u) == 0 ? 1 : 0;
   if (h->mono) {
     k_step<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io);
   } else {
@@ -1324,6 +1362,39 @@ int hk_debug_lane_trace(hk_env* h, uint32_t* out_host, int64_t n_words) {
 }
 
 int hk_launches_per_step(const hk_env* h) { return h ? h->launches : 0; }
+
+int hk_kernel_timing(hk_env* h, int enable) {
+  if (!h) return fail(HK_E_INVALID, "hk_kernel_timing: NULL handle");
+  DeviceGuard guard(h->device);
+  const int total = hk_env::kTimedSteps * hk_env::kEventsPerStep;
+  if (enable && !h->events) {
+    h->events = new cudaEvent_t[total];
+    for (int k = 0; k < total; ++k) HK_CUDA(cudaEventCreate(&h->events[k]));
+  } else if (!enable && h->events) {
+    for (int k = 0; k < total; ++k) cudaEventDestroy(h->events[k]);
+    delete[] h->events;
+    h->events = nullptr;
+  }
+  h->timedSteps = 0;
+  return HK_OK;
+}
+
+int hk_kernel_times(hk_env* h, double* out_ms4, int64_t* steps_out) {
+  if (!h || !out_ms4) return fail(HK_E_INVALID, "hk_kernel_times: NULL argument");
+  if (!h->events) return fail(HK_E_INVALID, "hk_kernel_times: call hk_kernel_timing(env, 1) first");
+  DeviceGuard guard(h->device);
+  HK_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < 4; ++k) out_ms4[k] = 0.0;
+  for (int s = 0; s < h->timedSteps; ++s)
+    for (int k = 0; k < 4; ++k) {
+      float ms = 0.0f;
+      HK_CUDA(cudaEventElapsedTime(&ms, h->events[s * hk_env::kEventsPerStep + k], h->events[s * hk_env::kEventsPerStep + k + 1]));
+      out_ms4[k] += (double)ms;
+    }
+  if (steps_out) *steps_out = h->timedSteps;
+  h->timedSteps = 0;
+  return HK_OK;
+}
 
 int hk_stats_device_ptr(hk_env* h, double** out_dev) {
   if (!h || !out_dev) return fail(HK_E_INVALID, "hk_stats_device_ptr: NULL argument");

@@ -22,6 +22,7 @@ struct StepIO {
   float* final_obs;  // [n,18] or null
   int write;         // 0: suppress all per-tick outputs (inner ticks of hk_rollout)
   float* actBuf;     // [n,8] scratch: clipped actions k_fast computed for the envs it hands to the general tiers
+  int stageRows;     // k_fast: write obs / final_obs rows warp-cooperatively (needs 16-byte aligned row tensors)
 };
 
 HK_HD int pol2Of(const StepIO& io, size_t i) { return io.pol2v ? (int)io.pol2v[i] : io.pol2; }
@@ -47,10 +48,42 @@ HK_HD void writeRow18(float* dst, const float* o) {
   }
 }
 
+HK_HD void writeRow4(float* dst, float a, float b, float c, float d) {  // info rows are 16 B: one 128-bit store
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+#else
+  dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+#endif
+}
+
+// A warp's 32 observation rows (32 x 72 B = 2304 contiguous bytes when its envs are consecutive) staged in shared
+// memory as [lane][18] floats and written with 128-bit stores that cover the span front to back: 4.5 fully coalesced
+// 512-byte warp stores instead of nine 8-byte stores per lane at a 72-byte lane stride.  `mask` = lanes whose rows are
+// to be written; a float4 that straddles two rows (18 floats per row) degrades to the valid 8-byte half.  dst must be
+// 16-byte aligned (it is the row of a warp's first env: 2304 * k bytes into a 16-byte aligned tensor).
+#if defined(__CUDACC__)
+__device__ __forceinline__ void warpStoreRows18(float* __restrict__ dst, const float* __restrict__ stage, unsigned mask) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const int j = r * 32 + lane;  // float4 index within the warp's span of 144 float4
+    if (j < 144) {
+      const bool lo = (mask >> ((4 * j) / 18)) & 1u, hi = (mask >> ((4 * j + 2) / 18)) & 1u;
+      const float4 v = reinterpret_cast<const float4*>(stage)[j];
+      if (lo && hi) reinterpret_cast<float4*>(dst)[j] = v;
+      else if (lo) reinterpret_cast<float2*>(dst)[2 * j] = make_float2(v.x, v.y);
+      else if (hi) reinterpret_cast<float2*>(dst)[2 * j + 1] = make_float2(v.z, v.w);
+    }
+  }
+}
+#endif
+
 // everything after the physics of a tick: info/reward, outputs, statistics, auto-reset
-// `write` = false suppresses all per-tick outputs (fused rollout, all but the last tick)
+// `write` = false suppresses all per-tick outputs (fused rollout, all but the last tick).
+// deferRows != null (k_fast): the caller writes the obs row (and the final_obs row unless this env was reset here)
+// warp-cooperatively after the call; *deferRows is set when this call already wrote the env's terminal final_obs row.
 HK_HD_NOINLINE void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io, bool write,
-                      TickStats& st, int had1, int had2) {
+                      TickStats& st, int had1, int had2, bool* deferRows = nullptr) {
   double inf[4], inf2[4];
   getInfo(cfg, e, false, inf);
   getInfo(cfg, e, true, inf2);
@@ -66,25 +99,22 @@ HK_HD_NOINLINE void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64
   e.nVelIters = e.nToiEvents = e.nOverflow = 0;
   if (e.has1 == HK_MAX_TIME_KEEP_PUCK && had1 != HK_MAX_TIME_KEEP_PUCK) st.touch1 += 1;
   if (e.has2 == HK_MAX_TIME_KEEP_PUCK && had2 != HK_MAX_TIME_KEEP_PUCK) st.touch2 += 1;
+  const bool resetNow = e.done && (io.flags & 1);
+  if (deferRows) *deferRows = false;
   if (write) {
     if (io.reward) io.reward[i] = (float)r;
     if (io.reward2) io.reward2[i] = (float)r2;
     if (io.done) io.done[i] = e.done ? 1 : 0;
-    if (io.info) {
-      float* q = io.info + 4 * i;
-      q[0] = (float)inf[0]; q[1] = (float)inf[1]; q[2] = (float)inf[2]; q[3] = (float)inf[3];
-    }
-    if (io.info2) {
-      float* q = io.info2 + 4 * i;
-      q[0] = (float)inf2[0]; q[1] = (float)inf2[1]; q[2] = (float)inf2[2]; q[3] = (float)inf2[3];
-    }
-    if (io.final_obs) {
+    if (io.info) writeRow4(io.info + 4 * i, (float)inf[0], (float)inf[1], (float)inf[2], (float)inf[3]);
+    if (io.info2) writeRow4(io.info2 + 4 * i, (float)inf2[0], (float)inf2[1], (float)inf2[2], (float)inf2[3]);
+    if (io.final_obs && (!deferRows || resetNow)) {
       float o[18];
       getObs(e, o);
       writeRow18(io.final_obs + 18 * i, o);
+      if (deferRows) *deferRows = true;
     }
   }
-  if (e.done && (io.flags & 1)) {
+  if (resetNow) {
     st.episodes += 1;
     if (e.winner == 1) st.wins += 1;
     else if (e.winner == -1) st.losses += 1;
@@ -97,7 +127,7 @@ HK_HD_NOINLINE void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64
   }
   if (write) {
     float o[18];
-    if (io.obs) {
+    if (io.obs && !deferRows) {
       getObs(e, o);
       writeRow18(io.obs + 18 * i, o);
     }
@@ -126,7 +156,7 @@ HK_HD bool envTick(const Scene& S, const Config& cfg, const Cache& cache, Env& e
 
 // fast tick: returns false (e unusable, nothing written) if the env needs the general path this tick
 HK_HD bool envTickFast(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io,
-                       bool write, TickStats& st) {
+                       bool write, TickStats& st, bool* deferRows = nullptr) {
   float a[8];
   policyActions(cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, i), a);
   const int had1 = e.has1, had2 = e.has2;
@@ -136,7 +166,7 @@ HK_HD bool envTickFast(const Scene& S, const Config& cfg, Env& e, uint64_t env_i
     }
     return false;
   }
-  tickFinish(S, cfg, e, env_id, i, io, write, st, had1, had2);
+  tickFinish(S, cfg, e, env_id, i, io, write, st, had1, had2, deferRows);
   return true;
 }
 

@@ -246,6 +246,55 @@ class HockeyVecEnv:
                                       self._stream()))
         return self.obs, self.reward, self.done, self.truncated, self._info_dict(self.info)
 
+    # -- host-agent path: results straight into pinned host memory -------------------------------------------------
+    def host_buffers(self, final_obs=False):
+        """One pinned host allocation laid out as obs [N,18] f32 | reward [N] f32 | info [N,4] f32 | done [N] u8
+        (| final_obs [N,18] f32), every section 256-byte aligned, plus a device record of the same layout and a device
+        action buffer: what `step_host` fills.  Returns a dict of views."""
+        n = self.num_envs
+        up = lambda x: (x + 255) // 256 * 256
+        sizes = [("obs", 72 * n), ("reward", 4 * n), ("info", 16 * n), ("done", n)] + ([("final_obs", 72 * n)] if final_obs else [])
+        off, total = {}, 0
+        for k, b in sizes:
+            off[k] = total
+            total += up(b)
+        raw = torch.empty(total, dtype=torch.uint8).pin_memory()
+        dev = torch.empty(total, dtype=torch.uint8, device=self.device)
+
+        def views(buf):
+            v = {"obs": buf[off["obs"]:off["obs"] + 72 * n].view(torch.float32).view(n, 18),
+                 "reward": buf[off["reward"]:off["reward"] + 4 * n].view(torch.float32),
+                 "info": buf[off["info"]:off["info"] + 16 * n].view(torch.float32).view(n, 4),
+                 "done": buf[off["done"]:off["done"] + n]}
+            v["final_obs"] = buf[off["final_obs"]:off["final_obs"] + 72 * n].view(torch.float32).view(n, 18) if final_obs else None
+            return v
+        rec = {"raw": raw, "host": views(raw), "dev_raw": dev, "dev": views(dev), "bytes": sum(b for _, b in sizes),
+               "act": torch.empty((n, 8 if self.action_dim == 8 else 4), dtype=torch.float32, device=self.device)}
+        return rec
+
+    def host_bytes_per_step(self, final_obs=False):
+        return self.num_envs * (72 + 4 + 16 + 1 + (72 if final_obs else 0))
+
+    def step_host(self, action_host, rec, sync=True, zero_copy=True):
+        """One tick for a HOST-side agent: `action_host` (pinned float32 [N,4|8]) is copied to the device, the tick runs,
+        and obs / reward / info / done (/ final_obs) arrive in `rec["host"]` (pinned, see host_buffers).
+        zero_copy=True: the kernels store their outputs straight into the mapped pinned record, so the transfer over
+        PCIe overlaps the tick (the fast tier's rows travel while the general tier still runs) and no D2H copy follows;
+        zero_copy=False: outputs go to the device record and ONE D2H copy moves it.  sync=True waits for the results."""
+        rec["act"].copy_(action_host, non_blocking=True)
+        out = rec["host"] if zero_copy else rec["dev"]
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_step(self._h, _ptr(rec["act"]), rec["act"].shape[1], self.p1, self.p2,
+                                      _lib.STEP_AUTORESET if self.auto_reset else 0,
+                                      _ptr(out["obs"]), None, _ptr(out["reward"]), None, _ptr(out["done"]), _ptr(out["info"]),
+                                      None, _ptr(out["final_obs"]), self._stream()))
+        if not zero_copy:
+            rec["raw"].copy_(rec["dev_raw"], non_blocking=True)
+        if sync:
+            torch.cuda.current_stream(self.device).synchronize()
+        h = rec["host"]
+        return h["obs"], h["reward"], h["done"], self.truncated, self._info_dict(h["info"])
+
     def rollout(self, k_steps, p1="strong", p2="strong", write_obs=False):
         """k fused ticks in one launch with in-kernel policies and auto-reset (hk_rollout)."""
         with torch.cuda.device(self.device):
@@ -310,8 +359,21 @@ class HockeyVecEnv:
             _lib.check(self.L.hk_get_stats(self._h, out, self._stream()))
         v = np.array(out[:], dtype=np.float64)
         keys = ["episodes", "wins", "losses", "draws", "env_steps", "sum_return_p1", "sum_return_p2", "sum_return_sq_p1",
-                "sum_episode_len", "touches_p1", "touches_p2", "velocity_iterations", "toi_events", "overflows"]
+                "sum_episode_len", "touches_p1", "touches_p2", "velocity_iterations", "toi_events", "overflows", "general_tier_env_steps"]
         return dict(zip(keys, v.tolist()))
+
+    def kernel_timing(self, enable=True):
+        """Record CUDA events around every kernel of the following ticks (measurement only, see hk_kernel_timing)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_kernel_timing(self._h, int(bool(enable))))
+
+    def kernel_times(self):
+        """({'k_fast': ms, 'k_touch': ms, 'k_general': ms, 'k_general2': ms} summed over the recorded ticks, ticks)."""
+        out = (C.c_double * 4)()
+        steps = C.c_int64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.hk_kernel_times(self._h, out, C.byref(steps)))
+        return dict(zip(("k_fast", "k_touch", "k_general", "k_general2"), list(out))), int(steps.value)
 
     def launches_per_step(self):
         """Kernels one step() launches (k_fast, k_touch and the general tier(s) of the cascade)."""

@@ -158,7 +158,8 @@ int hk_set_obs_state(hk_env* env, const float* obs18_dev, void* stream);
  * out_host[HK_STATS_DIM] doubles: 0 episodes, 1 wins(+1), 2 losses(-1), 3 draws, 4 env-steps,
  * 5 sum return p1, 6 sum return p2, 7 sum return^2 p1, 8 sum episode length, 9 puck touches p1,
  * 10 puck touches p2, 11 velocity-solver iterations executed, 12 TOI events, 13 contact-list
- * overflows (must be 0), 14-15 reserved.  Synchronises `stream`. */
+ * overflows (must be 0), 14 env-steps completed by the general tier(s) (the rest finished in the fast / touch tier),
+ * 15 reserved.  Synchronises `stream`. */
 int hk_get_stats(hk_env* env, double* out_host, void* stream);
 int hk_clear_stats(hk_env* env, void* stream);
 /* Device pointer to the HK_STATS_DIM accumulators (f64), for an NCCL all-reduce without a host hop. */
@@ -174,6 +175,13 @@ int hk_debug_phase_cycles(hk_env* env, double* out_host8);
 int hk_debug_lane_trace(hk_env* env, uint32_t* out_host, int64_t n_words);
 /* Kernels one hk_step launches on this handle (k_fast, k_touch, general tier(s)); for launch accounting. */
 int hk_launches_per_step(const hk_env* env);
+
+/* Measurement: per-kernel device times of the ticks that follow.  hk_kernel_timing(env, 1) makes every hk_step /
+ * hk_rollout tick record CUDA events on the launching stream around each kernel of the cascade (up to 2048 ticks; not
+ * graph-capturable while enabled); hk_kernel_times synchronises the device, returns the summed milliseconds of
+ * {k_fast, k_touch, general tier, second general tier} and the number of ticks they cover, and restarts the record. */
+int hk_kernel_timing(hk_env* env, int enable);
+int hk_kernel_times(hk_env* env, double* out_ms4, int64_t* steps_out);
 
 const char* hk_last_error(void);
 const char* hk_version(void);

@@ -356,30 +356,115 @@ def test_shard_invariance_gpu(oracle):
         assert sa[k] + sb[k] == s[k]
 
 
-def test_statistics_vs_notebook_10k_episodes(oracle):
-    """>= 10k episodes of strong-vs-strong BasicOpponent play on the GPU against the reference's recorded 1000-game
-    sample (Hockey-Env.ipynb cells 52-59): W/D/L 319/368/313, mean length 150.9, reward sums."""
+def test_statistics_vs_notebook_100k_episodes(oracle):
+    """>= 100k episodes of strong-vs-strong BasicOpponent play on the GPU against the reference's recorded 1000-game
+    sample (Hockey-Env.ipynb cells 52-59): W/D/L 319/368/313, 150,911 steps, reward sums, and the 18 column means of
+    all post-step observations (cell 54).  The notebook's numbers are ONE sample of 1000 games; their sampling spread is
+    estimated here from 128 disjoint groups of envs, each holding about as many steps as the notebook's sample, so every
+    comparison is a z-score against the empirical distribution of such samples (|z| < 4)."""
     import json
     import os
     import hockey_env_b200 as hk
     fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_fixtures.json")))["strong_vs_strong_1000_games"]
-    n = 8192
+    n, ticks, groups = 65536, 320, 128          # 128 groups x 512 envs x 320 ticks = 163,840 steps per group (notebook: 150,911)
     env = hk.HockeyVecEnv(n, device="cuda:0", seed=2024, p1="strong", p2="strong", want_agent_two=True)
     env.reset(one_starting=(torch.arange(n, device="cuda:0") % 2).to(torch.int8))
-    for _ in range(2600):
+    for _ in range(260):                        # de-synchronise the episodes first
         env.step()
+    env.clear_stats()
+    obs_sum = torch.zeros((n, 18), dtype=torch.float64, device="cuda:0")
+    r_sum = torch.zeros((n, 2), dtype=torch.float64, device="cuda:0")
+    wdl = torch.zeros((n, 3), dtype=torch.float64, device="cuda:0")
+    for _ in range(ticks):
+        obs, rew, done, _, info = env.step()
+        d = done.to(torch.bool)
+        # the notebook appends the obs returned by step(): the terminal one on the last tick of a game
+        obs_sum += torch.where(d[:, None], env.final_obs, obs).to(torch.float64)
+        r_sum[:, 0] += rew.to(torch.float64)
+        r_sum[:, 1] += env.reward2.to(torch.float64)
+        w = info["winner"]
+        wdl += torch.stack([(d & (w == 1)), (d & (w == 0)), (d & (w == -1))], 1).to(torch.float64)
     s = env.stats()
     ep = s["episodes"]
-    assert ep >= 10_000 and s["overflows"] == 0
-    for got, ref in ((s["wins"] / ep, fx["winners_plus1"] / 1000), (s["draws"] / ep, fx["winners_zero"] / 1000),
-                     (s["losses"] / ep, fx["winners_minus1"] / 1000)):
-        se = np.sqrt(ref * (1 - ref) / 1000 + ref * (1 - ref) / ep)
-        assert abs(got - ref) < 3.5 * se, (got, ref)
-    assert abs(s["sum_episode_len"] / ep - fx["total_steps"] / 1000) < 8.0
-    assert abs(s["wins"] - s["losses"]) / ep < 0.03
-    # reward sums per 1000 games (notebook: -4360 / -4368)
-    assert abs(1000 * s["sum_return_p1"] / ep - fx["reward_sums"][0]) < 500
-    assert abs(1000 * s["sum_return_p2"] / ep - fx["reward_sums"][1]) < 500
+    assert ep >= 100_000 and s["overflows"] == 0 and s["env_steps"] == n * ticks
+    assert int(wdl.sum().item()) == ep
+    g = lambda t: t.view(groups, n // groups, -1).sum(1).cpu().numpy()
+    steps_g = float(n // groups * ticks)
+    obs_g = g(obs_sum) / steps_g                                   # [groups, 18] column means per group
+    games_g = g(wdl).sum(1)                                        # games finished per group
+    wdl_g = g(wdl) / games_g[:, None]
+    len_g = steps_g / games_g
+    rew_g = g(r_sum) / games_g[:, None] * 1000.0                   # reward sums per 1000 games
+
+    def z(ref, sample):
+        return (ref - sample.mean()) / sample.std(ddof=1)
+    zs = {f"obs[{k}]": z(fx["obs_mean"][k], obs_g[:, k]) for k in range(18)}
+    zs["win"] = z(fx["winners_plus1"] / 1000, wdl_g[:, 0])
+    zs["draw"] = z(fx["winners_zero"] / 1000, wdl_g[:, 1])
+    zs["loss"] = z(fx["winners_minus1"] / 1000, wdl_g[:, 2])
+    zs["mean_len"] = z(fx["total_steps"] / 1000, len_g)
+    zs["reward_sum_p1"] = z(fx["reward_sums"][0], rew_g[:, 0])
+    zs["reward_sum_p2"] = z(fx["reward_sums"][1], rew_g[:, 1])
+    print({k: round(float(v), 2) for k, v in zs.items()})
+    bad = {k: float(v) for k, v in zs.items() if not abs(v) < 4.0}
+    assert not bad, bad
+    assert np.sqrt(np.mean(np.square(list(zs.values())))) < 2.0    # and no systematic shift: rms z over the 24 statistics
+    assert abs(s["wins"] - s["losses"]) / ep < 0.01                # the game is symmetric
+
+
+def test_seeded_reset_gpu(oracle):
+    """hk_reset_seeded through HockeyVecEnv.reset(seed=...) and HockeyEnv.reset(seed=...) (hockey_env.py:347)."""
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    n = 256
+    env, ora = _mk(hk, O, n, 1, 17, O.POL_STRONG, O.POL_STRONG)
+    for _ in range(25):
+        env.step()
+        ora.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+    seeds = np.arange(n, dtype=np.int64) % 16 + 5
+    seeds[3::5] = -1
+    obs, _ = env.reset(seed=torch.from_numpy(seeds))
+    o_obs = ora.reset(seeds=seeds)
+    assert np.array_equal(obs.cpu().numpy(), o_obs)
+    assert len(state_mismatches(ora.get_state(), _state(env))) == 0
+    a = obs.cpu().numpy()
+    assert np.array_equal(a[0, :16], a[16, :16]) and not np.array_equal(a[0, :16], a[1, :16])
+    obs2, _ = env.reset(seed=5)                                    # int: env i gets seed 5 + i
+    b = obs2.cpu().numpy()
+    assert np.array_equal(b[0, :16], a[0, :16]) and np.array_equal(b[1, :16], a[1, :16])
+    # single-env drop-in: same seed, same start; the reference's Evaluator relies on it (rl/utils/evaluator.py:18)
+    e1 = hk.HockeyEnv(mode=hk.Mode.TRAIN_DEFENSE, seed=1)
+    e2 = hk.HockeyEnv(mode=hk.Mode.TRAIN_DEFENSE, seed=99)
+    o1, _ = e1.reset(seed=1234)
+    o2, _ = e2.reset(seed=1234)
+    o3, _ = e2.reset(seed=1235)
+    assert np.array_equal(o1[:16], o2[:16]) and not np.array_equal(o2[:16], o3[:16])
+    e1.close(); e2.close()
+
+
+def test_step_host_matches_device_step():
+    """HockeyVecEnv.step_host (host-side agent: actions from pinned memory, results into the pinned packed record, by
+    zero-copy stores or by one D2H copy) returns exactly what step() leaves in the device tensors."""
+    import hockey_env_b200 as hk
+    n = 4096
+    envs = [hk.HockeyVecEnv(n, device="cuda:0", seed=6, p2="strong") for _ in range(3)]
+    recs = [None, envs[1].host_buffers(final_obs=True), envs[2].host_buffers(final_obs=True)]
+    g = torch.Generator()
+    g.manual_seed(0)
+    n_done = 0
+    for t in range(300):
+        a = (torch.rand((n, 4), generator=g) * 2 - 1).pin_memory()
+        obs, rew, done, _, info = envs[0].step(a.cuda())
+        for k, zc in ((1, True), (2, False)):
+            ho, hr, hd, _, hi = envs[k].step_host(a, recs[k], zero_copy=zc)
+            assert not ho.is_cuda and ho.is_pinned()
+            assert torch.equal(ho, obs.cpu()) and torch.equal(hr, rew.cpu()) and torch.equal(hd, done.cpu()), (t, zc)
+            assert torch.equal(hi["winner"], info["winner"].cpu()) and torch.equal(recs[k]["host"]["info"], envs[0].info.cpu())
+            assert torch.equal(recs[k]["host"]["final_obs"], envs[0].final_obs.cpu()), (t, zc)
+        n_done += int(done.sum().item())
+    assert n_done > n
+    assert envs[1].host_bytes_per_step() == n * 93
 
 
 def test_full_size_invariants():

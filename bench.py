@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-zero-copy", action="store_true", help="kernels store outputs straight into mapped pinned memory")
     ap.add_argument("--rollout-k", type=int, default=64, help="ticks per hk_rollout call of the fused-rollout leg (0 = skip)")
     args = ap.parse_args()
 
@@ -357,39 +358,59 @@ def main():
                    "k_steps": args.rollout_k, "calls": calls,
                    "note": "hk_rollout: in-kernel policies, auto-reset, statistics only (no per-tick outputs, no L2 flush)"}
 
-    # ---- end to end through the public API with HOST buffers: player-1 actions come from pinned host memory every
-    # tick, obs/reward/done/info go back to pinned host memory every tick (what a host-side agent would do).
+    # ---- end to end through the public API with HOST buffers.  Same workload as the device-timed leg: player 1's actions
+    # come from pinned host memory every tick (H2D inside the timed region), obs/reward/done/info go back to pinned host
+    # memory every tick, host sync every tick (what a host-side agent does).  To keep the dynamics those of the named
+    # workload, player 1's policy (the vectorised BasicOpponent / uniform noise / the actor) is run closed-loop ONCE,
+    # untimed, from a snapshot of the steady state and its actions are recorded to host memory; the timed pass restores
+    # the snapshot and replays them from the host, which reproduces that trajectory exactly.
     e2e = None
     if not args.no_e2e:
         p2 = c["p2"]
         e2e_env = hk.HockeyVecEnv(n, mode=mode, device=dev, seed=args.seed + 1, env_id_offset=rank * n, p2=p2)
-        e2e_env.reset(one_starting=(torch.arange(n, device=dev) % 2).to(torch.int8))
-        h_act = torch.empty((n, 4), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+        obs, _ = e2e_env.reset(one_starting=(torch.arange(n, device=dev) % 2).to(torch.int8))
+        if actor is not None:
+            policy = lambda o: actor(o)
+        elif c["p1"] == "random":
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(args.seed + rank)
+            policy = lambda o: torch.rand((n, 4), device=dev, generator=gen) * 2 - 1
+        else:
+            host_opp = hk.BasicOpponent(weak=c["p1"] == "weak")
+            policy = lambda o: host_opp.act(o)
+        e2e_warm = max(3, args.warmup)
+        e2e_steps = max(1, min(args.e2e_steps, (512 << 20) // (16 * n) - e2e_warm))
+        with torch.no_grad():
+            for _ in range(PREROLL_TICKS):
+                obs, *_ = e2e_env.step(policy(obs).contiguous())
+            snap = e2e_env.get_full_state()
+            h_acts = torch.empty((e2e_warm + e2e_steps, n, 4), dtype=torch.float32).pin_memory()
+            for k in range(e2e_warm + e2e_steps):
+                a = policy(obs).contiguous()
+                h_acts[k].copy_(a)
+                obs, *_ = e2e_env.step(a)
+        e2e_env.set_full_state(snap)
         host = e2e_env.host_buffers()
-
-        def e2e_tick():
-            e2e_env.step_host(h_act, host)  # H2D actions, tick, D2H packed outputs, stream sync
-
-        for _ in range(PREROLL_TICKS):
-            e2e_env.step_host(h_act, host, sync=False)
-        for _ in range(max(3, args.warmup)):
-            e2e_tick()
+        for k in range(e2e_warm):
+            e2e_env.step_host(h_acts[k], host, zero_copy=args.e2e_zero_copy)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.e2e_steps):
-            e2e_tick()
+        for k in range(e2e_steps):
+            e2e_env.step_host(h_acts[e2e_warm + k], host, zero_copy=args.e2e_zero_copy)  # H2D, tick, D2H, stream sync
         e1.record()
         barrier()
+        same = bool(torch.equal(host["host"]["obs"], obs.cpu()))  # the replay ended where the recording pass ended
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * args.e2e_steps / (float(t.item()) * 1e-3), "unit": "env-steps/s",
-               "h2d_bytes_per_step": h_act.numel() * 4, "d2h_bytes_per_step": e2e_env.host_bytes_per_step(),
-               "steps": args.e2e_steps,
-               "note": "HockeyVecEnv.step_host: player-1 actions from pinned host memory, obs/reward/done/info packed "
-                       f"to pinned host memory, host sync every tick; player 2 = in-kernel {p2}; after a "
-                       f"{PREROLL_TICKS}-tick pre-roll"}
+        e2e = {"value": world * n * e2e_steps / (float(t.item()) * 1e-3), "unit": "env-steps/s",
+               "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": e2e_env.host_bytes_per_step(),
+               "steps": e2e_steps, "ms_per_step": float(t.item()) / e2e_steps, "replay_matches_recording": same,
+               "note": "HockeyVecEnv.step_host: player-1 actions from pinned host memory (recorded closed-loop from the same "
+                       f"steady state: p1 = {c['p1']}), obs/reward/done/info "
+                       + ("stored by the kernels straight into" if args.e2e_zero_copy else "packed and copied with ONE D2H copy to")
+                       + f" pinned host memory, host sync every tick; player 2 = in-kernel {p2}"}
         e2e_env.close()
 
     # ---- end-of-run statistics: the only collective on this path (NCCL all-reduce of 16 doubles)

@@ -356,60 +356,52 @@ def test_shard_invariance_gpu(oracle):
         assert sa[k] + sb[k] == s[k]
 
 
-def test_statistics_vs_notebook_100k_episodes(oracle):
-    """>= 100k episodes of strong-vs-strong BasicOpponent play on the GPU against the reference's recorded 1000-game
-    sample (Hockey-Env.ipynb cells 52-59): W/D/L 319/368/313, 150,911 steps, reward sums, and the 18 column means of
-    all post-step observations (cell 54).  The notebook's numbers are ONE sample of 1000 games; their sampling spread is
-    estimated here from 128 disjoint groups of envs, each holding about as many steps as the notebook's sample, so every
-    comparison is a z-score against the empirical distribution of such samples (|z| < 4)."""
+def test_statistics_vs_notebook_500k_games(oracle):
+    """The reference's recorded 1000-game sample (Hockey-Env.ipynb cells 52-59: W/D/L 319/368/313, 150,911 steps,
+    reward sums, the 18 column means of all post-step observations) against 512 replicas of the same protocol on the
+    GPU: 2048 envs x 250 COMPLETE strong-vs-strong games (512,000 games), pooled 4 envs to a 1000-game replica.  Every
+    reference number must lie within 4 standard deviations of the replica distribution, and the rms z-score of the 24
+    statistics must stay near 1 (no systematic shift).  See notebook_protocol.py for why complete games matter."""
     import json
     import os
     import hockey_env_b200 as hk
+    import notebook_protocol as NP
     fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_fixtures.json")))["strong_vs_strong_1000_games"]
-    n, ticks, groups = 65536, 320, 128          # 128 groups x 512 envs x 320 ticks = 163,840 steps per group (notebook: 150,911)
-    env = hk.HockeyVecEnv(n, device="cuda:0", seed=2024, p1="strong", p2="strong", want_agent_two=True)
-    env.reset(one_starting=(torch.arange(n, device="cuda:0") % 2).to(torch.int8))
-    for _ in range(260):                        # de-synchronise the episodes first
-        env.step()
-    env.clear_stats()
-    obs_sum = torch.zeros((n, 18), dtype=torch.float64, device="cuda:0")
-    r_sum = torch.zeros((n, 2), dtype=torch.float64, device="cuda:0")
-    wdl = torch.zeros((n, 3), dtype=torch.float64, device="cuda:0")
-    for _ in range(ticks):
+    n, quota = 2048, 250
+    dev = "cuda:0"
+    env = hk.HockeyVecEnv(n, device=dev, seed=2024, p1="strong", p2="strong", want_agent_two=True)
+    env.reset()                                  # constructor reset(True) + reset(): the first game is player 2's
+    games = torch.zeros(n, dtype=torch.int64, device=dev)
+    obs_sum = torch.zeros((n, 18), dtype=torch.float64, device=dev)
+    steps = torch.zeros((n, 1), dtype=torch.int64, device=dev)
+    wdl = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+    rsum = torch.zeros((n, 2), dtype=torch.float64, device=dev)
+    ticks = 0
+    while True:
         obs, rew, done, _, info = env.step()
+        ticks += 1
+        live = games < quota
         d = done.to(torch.bool)
-        # the notebook appends the obs returned by step(): the terminal one on the last tick of a game
-        obs_sum += torch.where(d[:, None], env.final_obs, obs).to(torch.float64)
-        r_sum[:, 0] += rew.to(torch.float64)
-        r_sum[:, 1] += env.reward2.to(torch.float64)
+        o = torch.where(d[:, None], env.final_obs, obs).to(torch.float64)   # step() returns the terminal obs on the last tick
+        lf = live.to(torch.float64)
+        obs_sum += o * lf[:, None]
+        steps += live[:, None].to(torch.int64)
+        rsum += torch.stack([rew, env.reward2], 1).to(torch.float64) * lf[:, None]
         w = info["winner"]
-        wdl += torch.stack([(d & (w == 1)), (d & (w == 0)), (d & (w == -1))], 1).to(torch.float64)
-    s = env.stats()
-    ep = s["episodes"]
-    assert ep >= 100_000 and s["overflows"] == 0 and s["env_steps"] == n * ticks
-    assert int(wdl.sum().item()) == ep
-    g = lambda t: t.view(groups, n // groups, -1).sum(1).cpu().numpy()
-    steps_g = float(n // groups * ticks)
-    obs_g = g(obs_sum) / steps_g                                   # [groups, 18] column means per group
-    games_g = g(wdl).sum(1)                                        # games finished per group
-    wdl_g = g(wdl) / games_g[:, None]
-    len_g = steps_g / games_g
-    rew_g = g(r_sum) / games_g[:, None] * 1000.0                   # reward sums per 1000 games
-
-    def z(ref, sample):
-        return (ref - sample.mean()) / sample.std(ddof=1)
-    zs = {f"obs[{k}]": z(fx["obs_mean"][k], obs_g[:, k]) for k in range(18)}
-    zs["win"] = z(fx["winners_plus1"] / 1000, wdl_g[:, 0])
-    zs["draw"] = z(fx["winners_zero"] / 1000, wdl_g[:, 1])
-    zs["loss"] = z(fx["winners_minus1"] / 1000, wdl_g[:, 2])
-    zs["mean_len"] = z(fx["total_steps"] / 1000, len_g)
-    zs["reward_sum_p1"] = z(fx["reward_sums"][0], rew_g[:, 0])
-    zs["reward_sum_p2"] = z(fx["reward_sums"][1], rew_g[:, 1])
-    print({k: round(float(v), 2) for k, v in zs.items()})
-    bad = {k: float(v) for k, v in zs.items() if not abs(v) < 4.0}
-    assert not bad, bad
-    assert np.sqrt(np.mean(np.square(list(zs.values())))) < 2.0    # and no systematic shift: rms z over the 24 statistics
-    assert abs(s["wins"] - s["losses"]) / ep < 0.01                # the game is symmetric
+        f = d & live
+        wdl += torch.stack([f & (w == 1), f & (w == 0), f & (w == -1)], 1).to(torch.float64)
+        games += f
+        if ticks % 256 == 0 and bool((games >= quota).all().item()):
+            break
+    assert env.stats()["overflows"] == 0
+    reps = NP.replicas_from_env_sums(obs_sum.cpu().numpy(), steps.cpu().numpy(), wdl.cpu().numpy(), rsum.cpu().numpy(), quota)
+    z = NP.zscores(fx, reps)
+    print({k: round(float(v), 2) for k, v in zip(NP.STAT_NAMES, z)})
+    assert reps.shape == (512, 24)
+    assert np.all(np.abs(z) < 4.0), {k: float(v) for k, v in zip(NP.STAT_NAMES, z) if abs(v) >= 4.0}
+    assert np.sqrt(np.mean(z ** 2)) < 1.6
+    m = reps.mean(0)
+    assert abs(m[19] - m[21]) < 3.0              # side symmetry: wins - losses per 1000 games (sd of the mean ~ 1)
 
 
 def test_seeded_reset_gpu(oracle):

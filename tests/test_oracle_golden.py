@@ -125,3 +125,38 @@ def test_strong_vs_strong_statistics_match_notebook(oracle):
         assert abs(got - ref) < 3.5 * se, (got, ref)
     assert abs(s[8] / ep - fx["total_steps"] / 1000) < 8.0    # mean episode length 150.9 (per-game std ~ 90)
     assert abs(s[1] / ep - s[2] / ep) < 0.04                  # side symmetry
+
+
+def test_notebook_1000_game_protocol(oracle):
+    """The notebook's 1000-game sample (cells 52-59: steps, 18 obs column means, winners, reward sums) against the
+    sampling distribution of the same protocol on the oracle: 250 envs x 100 complete games = 25 replicas of 1000 games
+    (see notebook_protocol.py).  A 2048-env x 250-game version runs on the GPU tier; a 256-replica run of this check
+    (scripts/notebook_distribution.py) puts all 24 reference values within 1.6 standard deviations."""
+    import notebook_protocol as NP
+    O = oracle
+    n, quota = 250, 100
+    b = O.OracleBatch(n, mode=O.MODE_NORMAL, seed=5, n_threads=min(8, os.cpu_count() or 1))
+    b.reset()  # the constructor's reset(one_starts=True), then reset(): the first game starts with player 2's puck
+    games = np.zeros(n, np.int64)
+    obs_sum, steps, wdl, rsum = np.zeros((n, 18)), np.zeros((n, 1), np.int64), np.zeros((n, 3)), np.zeros((n, 2))
+    while (games < quota).any():
+        ro = b.step(None, O.POL_STRONG, O.POL_STRONG, O.STEP_AUTORESET)
+        live = games < quota
+        d = ro["done"].astype(bool)
+        o = np.where(d[:, None], ro["final_obs"], ro["obs"]).astype(np.float64)
+        obs_sum[live] += o[live]
+        steps[live] += 1
+        rsum[live, 0] += ro["reward"][live]
+        rsum[live, 1] += ro["reward2"][live]
+        w = ro["info"][:, 0]
+        f = d & live
+        wdl[f & (w == 1), 0] += 1
+        wdl[f & (w == 0), 1] += 1
+        wdl[f & (w == -1), 2] += 1
+        games += f
+    reps = NP.replicas_from_env_sums(obs_sum, steps, wdl, rsum, quota)
+    z = NP.zscores(FIX["strong_vs_strong_1000_games"], reps)
+    print({k: round(float(v), 2) for k, v in zip(NP.STAT_NAMES, z)})
+    assert reps.shape == (25, 24)
+    assert np.all(np.abs(z) < 4.5), {k: float(v) for k, v in zip(NP.STAT_NAMES, z) if abs(v) >= 4.5}
+    assert np.sqrt(np.mean(z ** 2)) < 1.8   # no systematic shift (expected rms ~ 1)

@@ -82,6 +82,10 @@ __device__ __forceinline__ double warpSumD(double v) {
   return v;
 }
 // per-env contact reductions -> warp shuffles/redux, one atomic per warp and statistic
+// The accumulators are replicated kStatsRows times (row = block index mod kStatsRows) so that the end-of-warp flushes of a
+// whole grid do not queue up on sixteen addresses; readers sum the rows (k_sum_stats).
+constexpr int kStatsRows = 64;
+__device__ __forceinline__ double* statsRow(double* gstats) { return gstats + HK_STATS_DIM * (blockIdx.x & (kStatsRows - 1)); }
 __device__ __forceinline__ void flushStats(double* gstats, const TickStats& st) {
   const int lane = threadIdx.x & 31;
   flushInt(gstats, 4, st.steps, lane);
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(kBlock) k_step(KParams P, StepIO io) {
     envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, true, st);
     storeEnv(P.core, P.n, i, e);
   }
-  flushStats(P.stats, st);
+  flushStats(statsRow(P.stats), st);
 }
 
 // ---- the per-tick pipeline: k_fast over all envs, then the general path over the queues (three-tier cascade) ----------------
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast(KParams P, StepIO io) {
       }
     }
   }
-  flushStats(P.stats, st);
+  flushStats(statsRow(P.stats), st);
 }
 
 // Touch tier: work class 0 of k_fast's queue (puck x racket contact ticks, i.e. every keep/shoot tick).  One contact,
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(kBlock) k_touch(KParams P, StepIO io) {
     base = __shfl_sync(0xffffffffu, base, 0);
     if (need) P.queue[(int64_t)(Q_CLASSES - 1) * P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
   }
-  flushStats(P.stats, st);
+  flushStats(statsRow(P.stats), st);
 }
 
 // Tier 1 and 2 of the cascade run the same general path (hk::envTick) over compacted queues:
@@ -309,6 +313,367 @@ __host__ __device__ constexpr size_t rawBytes(int envLanes) {  // dynamic shared
   const size_t toi = (sizeof(ToiTask) + sizeof(float)) * (size_t)envLanes * kTasksPerLane;
   return solve > toi ? solve : toi;
 }
+struct GenStamps {  // diagnostics: clock stamps of the phase boundaries of one general tick
+  long long tc0, tc1, tc2, tc3, stampB, stampV, stampT;
+};
+// barrier among the threads that walk a general tick together: the whole block (k_general), or the general team of the
+// fused rollout kernel (its first `nthr` threads; the other warps of that block run fast ticks meanwhile)
+template <bool TEAM>
+__device__ __forceinline__ void teamSync(int nthr) {
+  if (TEAM) asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory");
+  else __syncthreads();
+}
+// One general tick for up to `envWarps` warps of envs (lane = env: `valid`, state index `i`, work class `cls`), walked
+// phase by phase by `nthr` threads (threads 0 .. nthr-1 of the block, all of which must call this).
+template <int TIER, bool TEAM>
+__device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, const Scene& S, unsigned char* sRaw, const bool valid,
+                                            const int64_t i, const int cls, const bool envWarp, const int64_t gw, const int unlimited,
+                                            const int phaseSync, const int envWarps, const int nthr, const bool laneWrite,
+                                            TickStats& st, bool& need, GenStamps& gs, unsigned long long* sSlowUnitP, unsigned* sFin) {
+  const int envLanes = envWarps << 5;
+  tickStatsZero(st);
+  need = false;
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  // ---- the tick, phase by phase for the whole block (same code region at the same time on this SM) ----
+  Env e;
+  Cache cache;
+  cache.base = P.cache + i;
+  cache.stride = (size_t)P.n;
+  int had1 = 0, had2 = 0;
+  const uint64_t env_id = (uint64_t)(P.env_id_offset + i);
+  const float dt = (float)(1.0 / HK_FPS);
+  long long& tc0 = gs.tc0; tc0 = clock64();
+  if (valid) {  // phase 1: policy, forces, keep/shoot, Collide
+    loadEnv(P.core, P.n, i, e);
+    float a[8];
+    if (io.actBuf) {  // k_fast already ran the controllers for this tick
+      const float4* ab = reinterpret_cast<const float4*>(io.actBuf + 8 * i);
+      float4 lo = ab[0], hi = ab[1];
+      a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
+      policyAdvancePhases(P.cfg, e, env_id, io.pol1, pol2Of(io, (size_t)i));
+    } else {
+      policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, (size_t)i), a);
+    }
+    had1 = e.has1;
+    had2 = e.has2;
+    e.sweepBudget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
+    e.allowToiEvents = TIER != 1 || unlimited;
+    e.aborted = false;
+    envStepActions(S, P.cfg, e, a);
+    worldStepCollide(S, P.cfg, cache, e);
+  }
+  const long long tw1 = clock64();
+  // phaseSync bit 0/1/2: block-wide barrier after Collide / after the island solve / after SolveTOI.  They keep the
+  // warps of an SM in the same code region (shared instruction fetch); they are not needed for correctness.
+  if (phaseSync & 1) teamSync<TEAM>(nthr);
+  long long& tc1 = gs.tc1; tc1 = clock64();
+  // ---- phase 2: island solve.  The velocity iterations of the whole block are pooled (see SolveTask): every lane files
+  // its solve by loop shape, the warps of the block (helpers included) take one unit of one shape at a time.
+  IslandCtx ctx;
+  ctx.nvc = 0;
+  long long &stampB = gs.stampB, &stampV = gs.stampV, &stampT = gs.stampT;  // diagnostics: block-level stamps inside phases 2 and 3
+  stampB = stampV = stampT = 0;
+  if (valid) solveIslandsBegin(S, cache, e, dt, ctx);
+  {
+    SolveTask* mtasks = reinterpret_cast<SolveTask*>(sRaw);
+    Solve2Task* s2tasks = reinterpret_cast<Solve2Task*>(sRaw + kRawMulti);
+    const int cap2 = twoPointSlots(envLanes);
+    Solve1Task* s1tasks = reinterpret_cast<Solve1Task*>(sRaw + kRawMulti + sizeof(Solve2Task) * (size_t)cap2);
+    // counts: multi kinds 1..8, one contact x 1 point, one contact x 2 points, all multi-contact slots handed out
+    __shared__ int sKindCount[HK_MULTI_KINDS + 3];
+    __shared__ unsigned short sList[2][kSlowBlock];  // one-point tasks still unfinished after a round (double buffer)
+    __shared__ int sRound[5];                        // their count per round
+    if (threadIdx.x < HK_MULTI_KINDS + 3) sKindCount[threadIdx.x] = 0;
+    if (threadIdx.x < 5) sRound[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *sSlowUnitP = 0;
+    teamSync<TEAM>(nthr);
+    stampB = clock64();
+    const int nwarps = nthr >> 5;
+    const int budget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
+    const bool pool1 = (phaseSync & 8) != 0;  // also pool the single-contact solves
+    int kind = 0, slot = 0;  // kind 1..HK_MULTI_KINDS: multi; then single contact, 1 point; single contact, 2 points
+    if (valid && ctx.nvc >= 2) {
+      kind = solveKind(ctx.vcs, ctx.nvc);
+      if (kind) {
+        slot = atomicAdd(&sKindCount[HK_MULTI_KINDS + 2], 1);
+        if (slot >= kMultiSlots) kind = 0;  // no room: solved in place
+        else atomicAdd(&sKindCount[kind - 1], 1);
+      }
+    } else if (valid && ctx.nvc == 1 && pool1) {
+      kind = HK_MULTI_KINDS + ctx.vcs[0].count;
+      slot = atomicAdd(&sKindCount[kind - 1], 1);
+      if (kind == HK_MULTI_KINDS + 2 && slot >= cap2) kind = 0;
+    }
+    if (kind == HK_MULTI_KINDS + 1) {
+      Solve1Task& t = s1tasks[slot];
+      t.vc = vc1Of(ctx.vcs[0]);
+      t.A = loadVel(e, ctx.vcs[0].bA);
+      t.B = loadVel(e, ctx.vcs[0].bB);
+    } else if (kind == HK_MULTI_KINDS + 2) {
+      Solve2Task& t = s2tasks[slot];
+      t.vc = ctx.vcs[0];
+      t.A = loadVel(e, ctx.vcs[0].bA);
+      t.B = loadVel(e, ctx.vcs[0].bB);
+    } else if (kind) {
+      SolveTask& t = mtasks[slot];
+      t.kind = kind;
+      for (int k = 0; k < ctx.nvc; ++k) t.vcs[k] = ctx.vcs[k];
+      t.v.b0 = loadVel(e, 0);
+      t.v.b1 = loadVel(e, 1);
+      t.v.b2 = loadVel(e, 2);
+    }
+    teamSync<TEAM>(nthr);
+    {
+      // unit list, identical in every warp: the multi-contact shapes that have tasks (heaviest loops first), then the
+      // 2-point chunks, then the 1-point chunks; spare warps split the 1-point tasks into smaller chunks
+      const int n1 = sKindCount[HK_MULTI_KINDS], n2 = min(sKindCount[HK_MULTI_KINDS + 1], cap2);
+      const int nMulti = min(sKindCount[HK_MULTI_KINDS + 2], kMultiSlots);
+      int nm = 0, mk_[HK_MULTI_KINDS];
+#pragma unroll
+      for (int q = 0; q < HK_MULTI_KINDS; ++q) {
+        const int k = q == 0 ? 4 : (q == 1 ? 6 : (q == 2 ? 7 : (q == 3 ? 8 : (q == 4 ? 2 : (q == 5 ? 3 : (q == 6 ? 5 : 1))))));
+        if (sKindCount[k - 1] > 0) mk_[nm++] = k;
+      }
+      const int c2 = (n2 + 31) >> 5;
+      int c1 = (n1 + 31) >> 5;
+      const int spare = nwarps - nm - c2;
+      if (spare > c1) c1 = min(spare, (n1 + 3) >> 2);
+      const int units = (phaseSync & 16) ? nm + c2 : nm + c2 + c1;
+      // Re-packed one-point rounds (phaseSync bit 4): 92 % of the one-point solves end within ~30 sweeps, 8 % creep to
+      // 180, so a chunk's lanes mostly idle behind its slowest one.  The warps that hold no multi-contact / two-point
+      // unit run the one-point tasks in rounds of sweeps [0,12) [12,24) [24,48) [48,180) and re-pack the unfinished
+      // tasks densely between rounds (exact: see runVelocityIterations1Range); they meet at a named barrier of their
+      // own while the other warps work through the heavy units.
+      const int wHeavy = !(phaseSync & 16) || units == 0 || nwarps == 1 ? 0 : min(units, max(1, nwarps / 2));
+      const int uStride = (phaseSync & 16) ? max(wHeavy, 1) : nwarps;
+      const bool heavyWarp = !(phaseSync & 16) || wib < wHeavy || nwarps == 1;
+      // first round: unit w -> warp w; further rounds run backwards (the first warps hold the heavy multi-contact loops)
+      for (int r = 0, u = wib; heavyWarp && u < units; ++r, u = r * uStride + ((r & 1) ? uStride - 1 - wib : wib)) {
+        const long long tu0 = P.trace ? clock64() : 0;
+        int utype = 10;  // diagnostics: 1..8 multi-contact shape, 9 two-point chunk, 10 one-point chunk, 11 in place
+        if (u < nm) {
+          utype = mk_[u];
+          const int k = mk_[u];
+          // this shape's tasks among the block's multi-contact slots: lane l takes the l-th of them
+          const unsigned mine = __ballot_sync(0xffffffffu, lane < nMulti && mtasks[lane < nMulti ? lane : 0].kind == k);
+          if (lane < __popc(mine)) {
+            SolveTask& t = mtasks[__fns(mine, 0, lane + 1)];
+            VelTriple v = t.v;
+            int sweeps = 0;
+            t.result = runVelocityIterationsKind(k, t.vcs, v, budget, 6 * 30, &sweeps);
+            t.v = v;
+            t.sweeps = sweeps;
+          }
+        } else if (u < nm + c2) {
+          const int j = ((u - nm) << 5) + lane;
+          if (j < n2) {
+            Solve2Task& t = s2tasks[j];
+            Vel A = t.A, B = t.B;
+            int sweeps = 0;
+            t.result = runVelocityIterations2Core(t.vc, A, B, budget, 6 * 30, &sweeps);
+            t.A = A;
+            t.B = B;
+            t.sweeps = sweeps;
+          }
+        } else {
+          const int c = u - nm - c2;
+          const int lo = (int)(((long long)n1 * c) / c1), hi = (int)(((long long)n1 * (c + 1)) / c1);
+          const int j = lo + lane;
+          if (j < hi) {
+            Solve1Task& t = s1tasks[j];
+            Vel A = t.A, B = t.B;
+            int sweeps = 0;
+            t.result = runVelocityIterations1Core(t.vc, A, B, budget, 6 * 30, &sweeps);
+            t.A = A;
+            t.B = B;
+            t.sweeps = sweeps;
+          }
+        }
+        if (u >= nm && u < nm + c2) utype = 9;
+        if (P.trace && lane == 0) atomicMax(sSlowUnitP, ((unsigned long long)(clock64() - tu0) << 8) | (unsigned)utype);
+      }
+      if ((phaseSync & 16) && wib >= wHeavy) {
+        const long long tu0 = P.trace ? clock64() : 0;
+        const int w1 = nwarps - wHeavy, myw = wib - wHeavy;
+        int nA = n1, it0 = 0;
+        for (int r = 0; r < 4 && nA > 0; ++r) {
+          const int stop = r == 0 ? 12 : (r == 1 ? 24 : (r == 2 ? 48 : 6 * 30));
+          const int chunks = (nA + 31) >> 5;
+          for (int ch = myw; ch < chunks; ch += w1) {
+            const int j = (ch << 5) + lane;
+            if (j < nA) {
+              const int idx = r == 0 ? j : (int)sList[r & 1][j];
+              Solve1Task& t = s1tasks[idx];
+              Vel A = t.A, B = t.B;
+              int sweeps = 0;
+              const int res = runVelocityIterations1Range(t.vc, A, B, budget, 6 * 30, it0, stop, &sweeps);
+              t.A = A;
+              t.B = B;
+              if (res == HK_SOLVE_UNFINISHED) {
+                sList[(r + 1) & 1][atomicAdd(&sRound[r + 1], 1)] = (unsigned short)idx;
+              } else {
+                t.result = res;
+                t.sweeps = it0 + sweeps;
+              }
+            }
+          }
+          asm volatile("bar.sync 1, %0;" ::"r"(w1 * 32) : "memory");  // the one-point warps only
+          nA = sRound[r + 1];
+          it0 = stop;
+        }
+        if (P.trace && lane == 0) atomicMax(sSlowUnitP, ((unsigned long long)(clock64() - tu0) << 8) | 10u);
+      }
+    }
+    int itc = 0;
+    {
+      const long long tu0 = P.trace ? clock64() : 0;
+      const bool inPlace = valid && ctx.nvc > 0 && !kind;
+      if (inPlace) itc = runVelocityIterations(e, ctx.vcs, ctx.nvc, 6 * 30);
+      if (P.trace && __any_sync(0xffffffffu, inPlace) && lane == 0) atomicMax(sSlowUnitP, ((unsigned long long)(clock64() - tu0) << 8) | 11u);
+    }
+    teamSync<TEAM>(nthr);
+    stampV = clock64();
+    if (kind == HK_MULTI_KINDS + 1) {
+      const Solve1Task& t = s1tasks[slot];
+      ctx.vcs[0].pt[0].ni = t.vc.ni;
+      ctx.vcs[0].pt[0].ti = t.vc.ti;
+      storeVel(e, ctx.vcs[0].bA, t.A);
+      storeVel(e, ctx.vcs[0].bB, t.B);
+      e.nVelIters += (uint32_t)t.sweeps;
+      itc = t.result;
+    } else if (kind == HK_MULTI_KINDS + 2) {
+      const Solve2Task& t = s2tasks[slot];
+      ctx.vcs[0].pt[0].ni = t.vc.pt[0].ni;
+      ctx.vcs[0].pt[0].ti = t.vc.pt[0].ti;
+      ctx.vcs[0].pt[1].ni = t.vc.pt[1].ni;
+      ctx.vcs[0].pt[1].ti = t.vc.pt[1].ti;
+      storeVel(e, ctx.vcs[0].bA, t.A);
+      storeVel(e, ctx.vcs[0].bB, t.B);
+      e.nVelIters += (uint32_t)t.sweeps;
+      itc = t.result;
+    } else if (kind) {
+      const SolveTask& t = mtasks[slot];
+      for (int k = 0; k < ctx.nvc; ++k) {
+        ctx.vcs[k].pt[0].ni = t.vcs[k].pt[0].ni;
+        ctx.vcs[k].pt[0].ti = t.vcs[k].pt[0].ti;
+        if (ctx.vcs[k].count == 2) {
+          ctx.vcs[k].pt[1].ni = t.vcs[k].pt[1].ni;
+          ctx.vcs[k].pt[1].ti = t.vcs[k].pt[1].ti;
+        }
+      }
+      storeVel(e, 0, t.v.b0);
+      storeVel(e, 1, t.v.b1);
+      storeVel(e, 2, t.v.b2);
+      e.nVelIters += (uint32_t)t.sweeps;
+      itc = t.result;
+    }
+    if (valid) solveIslandsEnd(S, e, dt, 2 * 30, ctx, itc);
+  }
+  const long long tw2 = clock64();
+  if (phaseSync & 2) teamSync<TEAM>(nthr);
+  long long& tc2 = gs.tc2; tc2 = clock64();
+  // phase 3a-3c: first-pass TOI evaluations of the whole block as one task list, one task per thread
+  const bool wantToi = valid && !e.aborted && (e.exist & HK_PAIRS_TOI);
+  {
+    ToiTask* sTasks = reinterpret_cast<ToiTask*>(sRaw);  // worst case: every lane files all its tasks
+    float* sAlpha = reinterpret_cast<float*>(sRaw + sizeof(ToiTask) * (size_t)envLanes * kTasksPerLane);
+    __shared__ int sCount;
+    if (threadIdx.x == 0) sCount = 0;
+    teamSync<TEAM>(nthr);
+    ToiTask mine[kTasksPerLane];
+    int nMine = 0, base = 0;
+    if (wantToi) {
+      nMine = toiCollect(S, e, mine, kTasksPerLane);
+      if (nMine > 0) {
+        base = atomicAdd(&sCount, nMine);
+        for (int k = 0; k < nMine; ++k) sTasks[base + k] = mine[k];
+      }
+    }
+    teamSync<TEAM>(nthr);
+    const int total = sCount;
+    // tasks are dealt round-robin to the warps of the block (lane l of warp w takes task l * nwarps + w): the lanes
+    // of a warp diverge inside b2TimeOfImpact, so a warp's time grows with the number of tasks it holds
+    const int nwarps = nthr >> 5;
+    for (int t = lane * nwarps + (threadIdx.x >> 5); t < total; t += nthr) sAlpha[t] = toiTaskRun(S, sTasks[t]);
+    teamSync<TEAM>(nthr);
+    stampT = clock64();
+    for (int k = 0; k < nMine; ++k) {
+      e.toiPre[mine[k].pid] = sAlpha[base + k];
+      e.toiPreFlag |= 1u << mine[k].pid;
+    }
+  }
+  const long long tw3a = clock64();
+  if (wantToi) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3d: events (rare) on top of the pre-seeded results
+  const long long tw3 = clock64();
+  if (P.trace && TIER == 1 && envWarp && lane == 0 && gw < P.n / 32 + 8) {
+    uint32_t* w = P.trace + 4 * (size_t)gw;
+    w[0] = (uint32_t)(tw1 - tc0);
+    w[1] = (uint32_t)(tw2 - tc1);
+    w[2] = (uint32_t)(tw3a - tc2);
+    w[3] = (uint32_t)(tw3 - tw3a);
+  }
+  if (phaseSync & 4) teamSync<TEAM>(nthr);
+  long long& tc3 = gs.tc3; tc3 = clock64();
+  if (P.trace && (phaseSync & 4)) {  // diagnostics (HK_LANE_TRACE=1): block-wide max of per-lane TOI evaluation / event cycles
+    __shared__ unsigned long long sMaxEval, sMaxEvent;
+    if (threadIdx.x == 0) { sMaxEval = 0; sMaxEvent = 0; }
+    teamSync<TEAM>(nthr);
+    if (valid) {
+      atomicMax(&sMaxEval, (unsigned long long)e.dbgEvalClk);
+      atomicMax(&sMaxEvent, (unsigned long long)e.dbgEventClk);
+    }
+    teamSync<TEAM>(nthr);
+    if (threadIdx.x == 0 && TIER == 1) {
+      atomicAdd(&P.phaseClk[4], sMaxEval);
+      atomicAdd(&P.phaseClk[5], sMaxEvent);
+    }
+  }
+  if (P.trace && TIER == 1 && valid) {
+    uint32_t* rec = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)i;
+    rec[0] = (e.nVelIters & 0xFFFu) | ((e.nToiEvents & 0xFu) << 12) | ((uint32_t)(cls & 0xF) << 16) | ((e.dbgShape & 0xFFu) << 20) |
+             (e.aborted ? 0x80000000u : 0u);
+    rec[1] = (uint32_t)gw;
+  }
+  if (P.trace) {
+    if (threadIdx.x < 4) sFin[threadIdx.x] = 0;
+    teamSync<TEAM>(nthr);
+  }
+  const long long tf0 = clock64();
+  long long tf1 = tf0, tf2 = tf0;
+  if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
+    if (!e.aborted) {
+      worldStepFinish(cache, e);
+      envStepAfterWorld(P.cfg, e);
+      tf1 = clock64();
+      if (P.trace && e.done) atomicAdd(&sFin[3], 1u);
+      tickFinish(S, P.cfg, e, env_id, (size_t)i, io, laneWrite, st, had1, had2);
+      tf2 = clock64();
+      storeEnv(P.core, P.n, i, e);
+    } else {
+      need = true;
+    }
+  }
+  if (__any_sync(0xffffffffu, valid)) {
+    if (TIER == 1 && !TEAM) {
+      const unsigned m = __ballot_sync(0xffffffffu, need);
+      if (m) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&P.qctl[QC_COUNT2], (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (need) P.queue[(int64_t)Q_CLASSES * P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+      }
+    }
+    flushInt(statsRow(P.stats), 14, st.steps, lane);  // env-ticks completed by the general tiers (units of work per launch)
+    flushStats(statsRow(P.stats), st);
+  }
+  if (P.trace && valid) {
+    atomicMax(&sFin[0], (unsigned)(tf1 - tf0));
+    atomicMax(&sFin[1], (unsigned)(tf2 - tf1));
+    atomicMax(&sFin[2], (unsigned)(clock64() - tf2));
+  }
+}
+
 template <int TIER>
 __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps) {
   __shared__ Scene S;
@@ -403,346 +768,14 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
     }
   }
   TickStats st;
-  tickStatsZero(st);
   bool need = false;
-  // ---- the tick, phase by phase for the whole block (same code region at the same time on this SM) ----
-  Env e;
-  Cache cache;
-  cache.base = P.cache + i;
-  cache.stride = (size_t)P.n;
-  int had1 = 0, had2 = 0;
-  const uint64_t env_id = (uint64_t)(P.env_id_offset + i);
-  const float dt = (float)(1.0 / HK_FPS);
-  long long tc0 = clock64();
-  if (valid) {  // phase 1: policy, forces, keep/shoot, Collide
-    loadEnv(P.core, P.n, i, e);
-    float a[8];
-    if (io.actBuf) {  // k_fast already ran the controllers for this tick
-      const float4* ab = reinterpret_cast<const float4*>(io.actBuf + 8 * i);
-      float4 lo = ab[0], hi = ab[1];
-      a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
-      policyAdvancePhases(P.cfg, e, env_id, io.pol1, pol2Of(io, (size_t)i));
-    } else {
-      policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, (size_t)i), a);
-    }
-    had1 = e.has1;
-    had2 = e.has2;
-    e.sweepBudget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
-    e.allowToiEvents = TIER != 1 || unlimited;
-    e.aborted = false;
-    envStepActions(S, P.cfg, e, a);
-    worldStepCollide(S, P.cfg, cache, e);
-  }
-  const long long tw1 = clock64();
-  // phaseSync bit 0/1/2: block-wide barrier after Collide / after the island solve / after SolveTOI.  They keep the
-  // warps of an SM in the same code region (shared instruction fetch); they are not needed for correctness.
-  if (phaseSync & 1) __syncthreads();
-  long long tc1 = clock64();
-  // ---- phase 2: island solve.  The velocity iterations of the whole block are pooled (see SolveTask): every lane files
-  // its solve by loop shape, the warps of the block (helpers included) take one unit of one shape at a time.
-  IslandCtx ctx;
-  ctx.nvc = 0;
-  long long stampB = 0, stampV = 0, stampT = 0;  // diagnostics: block-level stamps inside phases 2 and 3
-  __shared__ unsigned long long sSlowUnit;       // diagnostics: (cycles << 8 | type) of the slowest pooled solve unit
-  if (valid) solveIslandsBegin(S, cache, e, dt, ctx);
-  {
-    SolveTask* mtasks = reinterpret_cast<SolveTask*>(sRaw);
-    Solve2Task* s2tasks = reinterpret_cast<Solve2Task*>(sRaw + kRawMulti);
-    const int cap2 = twoPointSlots(envLanes);
-    Solve1Task* s1tasks = reinterpret_cast<Solve1Task*>(sRaw + kRawMulti + sizeof(Solve2Task) * (size_t)cap2);
-    // counts: multi kinds 1..8, one contact x 1 point, one contact x 2 points, all multi-contact slots handed out
-    __shared__ int sKindCount[HK_MULTI_KINDS + 3];
-    __shared__ unsigned short sList[2][kSlowBlock];  // one-point tasks still unfinished after a round (double buffer)
-    __shared__ int sRound[5];                        // their count per round
-    if (threadIdx.x < HK_MULTI_KINDS + 3) sKindCount[threadIdx.x] = 0;
-    if (threadIdx.x < 5) sRound[threadIdx.x] = 0;
-    if (threadIdx.x == 0) sSlowUnit = 0;
-    __syncthreads();
-    stampB = clock64();
-    const int nwarps = blockDim.x >> 5;
-    const int budget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
-    const bool pool1 = (phaseSync & 8) != 0;  // also pool the single-contact solves
-    int kind = 0, slot = 0;  // kind 1..HK_MULTI_KINDS: multi; then single contact, 1 point; single contact, 2 points
-    if (valid && ctx.nvc >= 2) {
-      kind = solveKind(ctx.vcs, ctx.nvc);
-      if (kind) {
-        slot = atomicAdd(&sKindCount[HK_MULTI_KINDS + 2], 1);
-        if (slot >= kMultiSlots) kind = 0;  // no room: solved in place
-        else atomicAdd(&sKindCount[kind - 1], 1);
-      }
-    } else if (valid && ctx.nvc == 1 && pool1) {
-      kind = HK_MULTI_KINDS + ctx.vcs[0].count;
-      slot = atomicAdd(&sKindCount[kind - 1], 1);
-      if (kind == HK_MULTI_KINDS + 2 && slot >= cap2) kind = 0;
-    }
-    if (kind == HK_MULTI_KINDS + 1) {
-      Solve1Task& t = s1tasks[slot];
-      t.vc = vc1Of(ctx.vcs[0]);
-      t.A = loadVel(e, ctx.vcs[0].bA);
-      t.B = loadVel(e, ctx.vcs[0].bB);
-    } else if (kind == HK_MULTI_KINDS + 2) {
-      Solve2Task& t = s2tasks[slot];
-      t.vc = ctx.vcs[0];
-      t.A = loadVel(e, ctx.vcs[0].bA);
-      t.B = loadVel(e, ctx.vcs[0].bB);
-    } else if (kind) {
-      SolveTask& t = mtasks[slot];
-      t.kind = kind;
-      for (int k = 0; k < ctx.nvc; ++k) t.vcs[k] = ctx.vcs[k];
-      t.v.b0 = loadVel(e, 0);
-      t.v.b1 = loadVel(e, 1);
-      t.v.b2 = loadVel(e, 2);
-    }
-    __syncthreads();
-    {
-      // unit list, identical in every warp: the multi-contact shapes that have tasks (heaviest loops first), then the
-      // 2-point chunks, then the 1-point chunks; spare warps split the 1-point tasks into smaller chunks
-      const int n1 = sKindCount[HK_MULTI_KINDS], n2 = min(sKindCount[HK_MULTI_KINDS + 1], cap2);
-      const int nMulti = min(sKindCount[HK_MULTI_KINDS + 2], kMultiSlots);
-      int nm = 0, mk_[HK_MULTI_KINDS];
-#pragma unroll
-      for (int q = 0; q < HK_MULTI_KINDS; ++q) {
-        const int k = q == 0 ? 4 : (q == 1 ? 6 : (q == 2 ? 7 : (q == 3 ? 8 : (q == 4 ? 2 : (q == 5 ? 3 : (q == 6 ? 5 : 1))))));
-        if (sKindCount[k - 1] > 0) mk_[nm++] = k;
-      }
-      const int c2 = (n2 + 31) >> 5;
-      int c1 = (n1 + 31) >> 5;
-      const int spare = nwarps - nm - c2;
-      if (spare > c1) c1 = min(spare, (n1 + 3) >> 2);
-      const int units = (phaseSync & 16) ? nm + c2 : nm + c2 + c1;
-      // Re-packed one-point rounds (phaseSync bit 4): 92 % of the one-point solves end within ~30 sweeps, 8 % creep to
-      // 180, so a chunk's lanes mostly idle behind its slowest one.  The warps that hold no multi-contact / two-point
-      // unit run the one-point tasks in rounds of sweeps [0,12) [12,24) [24,48) [48,180) and re-pack the unfinished
-      // tasks densely between rounds (exact: see runVelocityIterations1Range); they meet at a named barrier of their
-      // own while the other warps work through the heavy units.
-      const int wHeavy = !(phaseSync & 16) || units == 0 || nwarps == 1 ? 0 : min(units, max(1, nwarps / 2));
-      const int uStride = (phaseSync & 16) ? max(wHeavy, 1) : nwarps;
-      const bool heavyWarp = !(phaseSync & 16) || wib < wHeavy || nwarps == 1;
-      // first round: unit w -> warp w; further rounds run backwards (the first warps hold the heavy multi-contact loops)
-      for (int r = 0, u = wib; heavyWarp && u < units; ++r, u = r * uStride + ((r & 1) ? uStride - 1 - wib : wib)) {
-        const long long tu0 = P.trace ? clock64() : 0;
-        int utype = 10;  // diagnostics: 1..8 multi-contact shape, 9 two-point chunk, 10 one-point chunk, 11 in place
-        if (u < nm) {
-          utype = mk_[u];
-          const int k = mk_[u];
-          // this shape's tasks among the block's multi-contact slots: lane l takes the l-th of them
-          const unsigned mine = __ballot_sync(0xffffffffu, lane < nMulti && mtasks[lane < nMulti ? lane : 0].kind == k);
-          if (lane < __popc(mine)) {
-            SolveTask& t = mtasks[__fns(mine, 0, lane + 1)];
-            VelTriple v = t.v;
-            int sweeps = 0;
-            t.result = runVelocityIterationsKind(k, t.vcs, v, budget, 6 * 30, &sweeps);
-            t.v = v;
-            t.sweeps = sweeps;
-          }
-        } else if (u < nm + c2) {
-          const int j = ((u - nm) << 5) + lane;
-          if (j < n2) {
-            Solve2Task& t = s2tasks[j];
-            Vel A = t.A, B = t.B;
-            int sweeps = 0;
-            t.result = runVelocityIterations2Core(t.vc, A, B, budget, 6 * 30, &sweeps);
-            t.A = A;
-            t.B = B;
-            t.sweeps = sweeps;
-          }
-        } else {
-          const int c = u - nm - c2;
-          const int lo = (int)(((long long)n1 * c) / c1), hi = (int)(((long long)n1 * (c + 1)) / c1);
-          const int j = lo + lane;
-          if (j < hi) {
-            Solve1Task& t = s1tasks[j];
-            Vel A = t.A, B = t.B;
-            int sweeps = 0;
-            t.result = runVelocityIterations1Core(t.vc, A, B, budget, 6 * 30, &sweeps);
-            t.A = A;
-            t.B = B;
-            t.sweeps = sweeps;
-          }
-        }
-        if (u >= nm && u < nm + c2) utype = 9;
-        if (P.trace && lane == 0) atomicMax(&sSlowUnit, ((unsigned long long)(clock64() - tu0) << 8) | (unsigned)utype);
-      }
-      if ((phaseSync & 16) && wib >= wHeavy) {
-        const long long tu0 = P.trace ? clock64() : 0;
-        const int w1 = nwarps - wHeavy, myw = wib - wHeavy;
-        int nA = n1, it0 = 0;
-        for (int r = 0; r < 4 && nA > 0; ++r) {
-          const int stop = r == 0 ? 12 : (r == 1 ? 24 : (r == 2 ? 48 : 6 * 30));
-          const int chunks = (nA + 31) >> 5;
-          for (int ch = myw; ch < chunks; ch += w1) {
-            const int j = (ch << 5) + lane;
-            if (j < nA) {
-              const int idx = r == 0 ? j : (int)sList[r & 1][j];
-              Solve1Task& t = s1tasks[idx];
-              Vel A = t.A, B = t.B;
-              int sweeps = 0;
-              const int res = runVelocityIterations1Range(t.vc, A, B, budget, 6 * 30, it0, stop, &sweeps);
-              t.A = A;
-              t.B = B;
-              if (res == HK_SOLVE_UNFINISHED) {
-                sList[(r + 1) & 1][atomicAdd(&sRound[r + 1], 1)] = (unsigned short)idx;
-              } else {
-                t.result = res;
-                t.sweeps = it0 + sweeps;
-              }
-            }
-          }
-          asm volatile("bar.sync 1, %0;" ::"r"(w1 * 32) : "memory");  // the one-point warps only
-          nA = sRound[r + 1];
-          it0 = stop;
-        }
-        if (P.trace && lane == 0) atomicMax(&sSlowUnit, ((unsigned long long)(clock64() - tu0) << 8) | 10u);
-      }
-    }
-    int itc = 0;
-    {
-      const long long tu0 = P.trace ? clock64() : 0;
-      const bool inPlace = valid && ctx.nvc > 0 && !kind;
-      if (inPlace) itc = runVelocityIterations(e, ctx.vcs, ctx.nvc, 6 * 30);
-      if (P.trace && __any_sync(0xffffffffu, inPlace) && lane == 0) atomicMax(&sSlowUnit, ((unsigned long long)(clock64() - tu0) << 8) | 11u);
-    }
-    __syncthreads();
-    stampV = clock64();
-    if (kind == HK_MULTI_KINDS + 1) {
-      const Solve1Task& t = s1tasks[slot];
-      ctx.vcs[0].pt[0].ni = t.vc.ni;
-      ctx.vcs[0].pt[0].ti = t.vc.ti;
-      storeVel(e, ctx.vcs[0].bA, t.A);
-      storeVel(e, ctx.vcs[0].bB, t.B);
-      e.nVelIters += (uint32_t)t.sweeps;
-      itc = t.result;
-    } else if (kind == HK_MULTI_KINDS + 2) {
-      const Solve2Task& t = s2tasks[slot];
-      ctx.vcs[0].pt[0].ni = t.vc.pt[0].ni;
-      ctx.vcs[0].pt[0].ti = t.vc.pt[0].ti;
-      ctx.vcs[0].pt[1].ni = t.vc.pt[1].ni;
-      ctx.vcs[0].pt[1].ti = t.vc.pt[1].ti;
-      storeVel(e, ctx.vcs[0].bA, t.A);
-      storeVel(e, ctx.vcs[0].bB, t.B);
-      e.nVelIters += (uint32_t)t.sweeps;
-      itc = t.result;
-    } else if (kind) {
-      const SolveTask& t = mtasks[slot];
-      for (int k = 0; k < ctx.nvc; ++k) {
-        ctx.vcs[k].pt[0].ni = t.vcs[k].pt[0].ni;
-        ctx.vcs[k].pt[0].ti = t.vcs[k].pt[0].ti;
-        if (ctx.vcs[k].count == 2) {
-          ctx.vcs[k].pt[1].ni = t.vcs[k].pt[1].ni;
-          ctx.vcs[k].pt[1].ti = t.vcs[k].pt[1].ti;
-        }
-      }
-      storeVel(e, 0, t.v.b0);
-      storeVel(e, 1, t.v.b1);
-      storeVel(e, 2, t.v.b2);
-      e.nVelIters += (uint32_t)t.sweeps;
-      itc = t.result;
-    }
-    if (valid) solveIslandsEnd(S, e, dt, 2 * 30, ctx, itc);
-  }
-  const long long tw2 = clock64();
-  if (phaseSync & 2) __syncthreads();
-  long long tc2 = clock64();
-  // phase 3a-3c: first-pass TOI evaluations of the whole block as one task list, one task per thread
-  const bool wantToi = valid && !e.aborted && (e.exist & HK_PAIRS_TOI);
-  {
-    ToiTask* sTasks = reinterpret_cast<ToiTask*>(sRaw);  // worst case: every lane files all its tasks
-    float* sAlpha = reinterpret_cast<float*>(sRaw + sizeof(ToiTask) * (size_t)envLanes * kTasksPerLane);
-    __shared__ int sCount;
-    if (threadIdx.x == 0) sCount = 0;
-    __syncthreads();
-    ToiTask mine[kTasksPerLane];
-    int nMine = 0, base = 0;
-    if (wantToi) {
-      nMine = toiCollect(S, e, mine, kTasksPerLane);
-      if (nMine > 0) {
-        base = atomicAdd(&sCount, nMine);
-        for (int k = 0; k < nMine; ++k) sTasks[base + k] = mine[k];
-      }
-    }
-    __syncthreads();
-    const int total = sCount;
-    // tasks are dealt round-robin to the warps of the block (lane l of warp w takes task l * nwarps + w): the lanes
-    // of a warp diverge inside b2TimeOfImpact, so a warp's time grows with the number of tasks it holds
-    const int nwarps = blockDim.x >> 5;
-    for (int t = lane * nwarps + (threadIdx.x >> 5); t < total; t += blockDim.x) sAlpha[t] = toiTaskRun(S, sTasks[t]);
-    __syncthreads();
-    stampT = clock64();
-    for (int k = 0; k < nMine; ++k) {
-      e.toiPre[mine[k].pid] = sAlpha[base + k];
-      e.toiPreFlag |= 1u << mine[k].pid;
-    }
-  }
-  const long long tw3a = clock64();
-  if (wantToi) solveTOI(S, P.cfg, cache, e, dt, 6 * 30);  // phase 3d: events (rare) on top of the pre-seeded results
-  const long long tw3 = clock64();
-  if (P.trace && TIER == 1 && envWarp && lane == 0 && gw < P.n / 32 + 8) {
-    uint32_t* w = P.trace + 4 * (size_t)gw;
-    w[0] = (uint32_t)(tw1 - tc0);
-    w[1] = (uint32_t)(tw2 - tc1);
-    w[2] = (uint32_t)(tw3a - tc2);
-    w[3] = (uint32_t)(tw3 - tw3a);
-  }
-  if (phaseSync & 4) __syncthreads();
-  long long tc3 = clock64();
-  if (P.trace && (phaseSync & 4)) {  // diagnostics (HK_LANE_TRACE=1): block-wide max of per-lane TOI evaluation / event cycles
-    __shared__ unsigned long long sMaxEval, sMaxEvent;
-    if (threadIdx.x == 0) { sMaxEval = 0; sMaxEvent = 0; }
-    __syncthreads();
-    if (valid) {
-      atomicMax(&sMaxEval, (unsigned long long)e.dbgEvalClk);
-      atomicMax(&sMaxEvent, (unsigned long long)e.dbgEventClk);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && TIER == 1) {
-      atomicAdd(&P.phaseClk[4], sMaxEval);
-      atomicAdd(&P.phaseClk[5], sMaxEvent);
-    }
-  }
-  if (P.trace && TIER == 1 && valid) {
-    uint32_t* rec = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)i;
-    rec[0] = (e.nVelIters & 0xFFFu) | ((e.nToiEvents & 0xFu) << 12) | ((uint32_t)(cls & 0xF) << 16) | ((e.dbgShape & 0xFFu) << 20) |
-             (e.aborted ? 0x80000000u : 0u);
-    rec[1] = (uint32_t)gw;
-  }
-  __shared__ unsigned sFin[4];  // diagnostics: block max of per-warp cycles in commit / tickFinish / store+flush, done lanes
-  if (P.trace) {
-    if (threadIdx.x < 4) sFin[threadIdx.x] = 0;
-    __syncthreads();
-  }
-  const long long tf0 = clock64();
-  long long tf1 = tf0, tf2 = tf0;
-  if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
-    if (!e.aborted) {
-      worldStepFinish(cache, e);
-      envStepAfterWorld(P.cfg, e);
-      tf1 = clock64();
-      if (P.trace && e.done) atomicAdd(&sFin[3], 1u);
-      tickFinish(S, P.cfg, e, env_id, (size_t)i, io, io.write != 0, st, had1, had2);
-      tf2 = clock64();
-      storeEnv(P.core, P.n, i, e);
-    } else {
-      need = true;
-    }
-  }
-  if (__any_sync(0xffffffffu, valid)) {
-    if (TIER == 1) {
-      const unsigned m = __ballot_sync(0xffffffffu, need);
-      if (m) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&P.qctl[QC_COUNT2], (unsigned)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (need) P.queue[(int64_t)Q_CLASSES * P.n + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
-      }
-    }
-    flushInt(P.stats, 14, st.steps, lane);  // env-ticks completed by the general tiers (units of work per launch)
-    flushStats(P.stats, st);
-  }
-  if (P.trace && valid) {
-    atomicMax(&sFin[0], (unsigned)(tf1 - tf0));
-    atomicMax(&sFin[1], (unsigned)(tf2 - tf1));
-    atomicMax(&sFin[2], (unsigned)(clock64() - tf2));
-  }
+  GenStamps gs;
+  __shared__ unsigned long long sSlowUnit;  // diagnostics: (cycles << 8 | type) of the slowest pooled solve unit
+  __shared__ unsigned sFin[4];              // diagnostics: block max of per-warp cycles in commit / tickFinish / store+flush, done lanes
+  generalTick<TIER, false>(P, io, S, sRaw, valid, i, cls, envWarp, gw, unlimited, phaseSync, envWarps, (int)blockDim.x, io.write != 0, st,
+                           need, gs, &sSlowUnit, sFin);
+  const long long tc0 = gs.tc0, tc1 = gs.tc1, tc2 = gs.tc2, tc3 = gs.tc3, stampB = gs.stampB, stampV = gs.stampV, stampT = gs.stampT;
+
   // the last block to finish re-arms this tier's queue(s) for the next tick
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -809,7 +842,191 @@ __global__ void __launch_bounds__(kBlock) k_rollout(KParams P, StepIO io, int k_
       envTick(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, s == k_steps - 1, st);
     storeEnv(P.core, P.n, i, e);
   }
-  flushStats(P.stats, st);
+  flushStats(statsRow(P.stats), st);
+}
+
+// ---- K fused ticks without a per-tick grid-wide join (hk_rollout) -------------------------------------------------------------
+// A block owns a chunk of envs for all K ticks and alternates, at its own pace, between two phases:
+//   * fast phase: its warps take batches of envs that are due for a fast attempt; every lane advances its env through up to
+//     `fastRun` consecutive contact-free ticks with the state held in registers (nothing is re-read between ticks; the last
+//     good state is written behind each tick) and re-queues it; an env whose proof fails is filed, by work class, for the
+//     general phase.  The phase ends when no env is due for a fast attempt: fast envs run ahead, up to K ticks.
+//   * general phase: rounds of one general tick (generalTick: Collide -> pooled island solve -> pooled TOI pass -> events
+//     -> finish) for up to 384 filed envs, class by class, until nothing is filed; the envs go back to the fast queue.
+// Envs are independent, so nothing waits for the slowest solve of "its" tick: the tick count of every env is tracked
+// individually, there is no grid-wide join, and one block's long solve does not hold up the other 147.  (Running the two
+// phases CONCURRENTLY on disjoint warps of the SM was measured and lost: the two code paths evict each other from the
+// instruction cache and a general round takes 2.4 M cycles instead of 0.9 M, profiles/README.md.)
+// Queues are rings in shared memory (publish = CAS on an empty slot, consume = reserve a range, then read each slot).
+constexpr int kFusedChunk = 512;  // envs per chunk (ring capacity)
+struct FusedShared {
+  int fastRing[kFusedChunk];
+  int genRing[Q_CLASSES][kFusedChunk];
+  int remaining[kFusedChunk];  // ticks each env of the chunk still has to make
+  unsigned fastHead, fastTail, genHead[Q_CLASSES], genTail[Q_CLASSES];
+  int doneCount, roundActive, batch;
+  int asgClass[kSlowBlock / 32], asgStart[kSlowBlock / 32], asgCount[kSlowBlock / 32];
+};
+__device__ __forceinline__ void ringPush(int* ring, unsigned* tail, int j) {
+  const unsigned slot = atomicAdd(tail, 1u) % kFusedChunk;
+  while (atomicCAS(&ring[slot], -1, j) != -1) {}  // the slot's previous entry (one lap ago) is consumed first
+}
+__device__ __forceinline__ int ringTake(int* ring, unsigned pos) {
+  const unsigned slot = pos % kFusedChunk;
+  int j;
+  while ((j = atomicExch(&ring[slot], -1)) < 0) {}  // reserved by a producer, not written yet
+  return j;
+}
+__global__ void __launch_bounds__(kSlowBlock, 1) k_rollout_fused(KParams P, StepIO io, int k_steps, int phaseSync, int chunk, int nChunks, int fastRun) {
+  __shared__ Scene S;
+  extern __shared__ __align__(16) unsigned char sRaw[];
+  __shared__ FusedShared F;
+  __shared__ unsigned long long sSlowUnit;
+  __shared__ unsigned sFin[4];
+  stageScene(&S);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  TickStats stFast;
+  tickStatsZero(stFast);
+  for (int c = blockIdx.x; c < nChunks; c += gridDim.x) {
+    const int64_t lo = (int64_t)c * chunk;
+    const int m = (int)(P.n - lo < (int64_t)chunk ? P.n - lo : (int64_t)chunk);
+    for (int j = threadIdx.x; j < kFusedChunk; j += blockDim.x) {
+      F.fastRing[j] = j < m ? j : -1;
+      F.remaining[j] = k_steps;
+#pragma unroll
+      for (int q = 0; q < Q_CLASSES; ++q) F.genRing[q][j] = -1;
+    }
+    if (threadIdx.x == 0) {
+      F.fastHead = 0;
+      F.fastTail = (unsigned)m;
+      for (int q = 0; q < Q_CLASSES; ++q) F.genHead[q] = F.genTail[q] = 0;
+      F.doneCount = 0;
+    }
+    __syncthreads();
+    for (;;) {
+      // ---- fast phase: until no env is due for a fast attempt ----
+      if (threadIdx.x == 0) {  // batches sized so that the envs due now are spread evenly over the warps
+        const int due = (int)(F.fastTail - F.fastHead), waves = (due + blockDim.x - 1) / (int)blockDim.x;
+        const int b = waves > 0 ? (due + nwarps * waves - 1) / (nwarps * waves) : 32;
+        F.batch = b < 8 ? 8 : (b > 32 ? 32 : b);
+      }
+      __syncthreads();
+      const long long tf0 = clock64();
+      int batches = 0;
+      for (;;) {
+        int take = 0;
+        unsigned h = 0;
+        if (lane == 0) {
+          for (;;) {
+            const unsigned hh = *((volatile unsigned*)&F.fastHead), tt = *((volatile unsigned*)&F.fastTail);
+            const int avail = (int)(tt - hh);
+            if (avail <= 0) { take = -1; break; }
+            const int want = avail < F.batch ? avail : F.batch;
+            if (atomicCAS(&F.fastHead, hh, hh + (unsigned)want) == hh) { h = hh; take = want; break; }
+          }
+        }
+        take = __shfl_sync(0xffffffffu, take, 0);
+        h = __shfl_sync(0xffffffffu, h, 0);
+        if (take < 0) break;
+        ++batches;
+        if (lane < take) {
+          const int j = ringTake(F.fastRing, h + (unsigned)lane);
+          const int64_t i = lo + j;
+          const uint64_t env_id = (uint64_t)(P.env_id_offset + i);
+          Env e;
+          loadEnv(P.core, P.n, i, e);
+          int rem = F.remaining[j];
+          for (int it = 0;; ++it) {
+            e.bailKind = 15;
+            if (!envTickFast(S, P.cfg, e, env_id, (size_t)i, io, rem == 1 && io.obs != nullptr, stFast)) {
+              F.remaining[j] = rem;
+              const int q = bailClass(e.bailKind);
+              ringPush(F.genRing[q], &F.genTail[q], j);  // read after the block-wide barrier that ends this phase
+              break;
+            }
+            --rem;
+            // the state as the next tick would load it: stored behind the tick, kept in registers for the next one
+            F4 g[CORE_GROUPS];
+            envToGroups(e, g);
+#pragma unroll
+            for (int k = 0; k < CORE_GROUPS; ++k) P.core[(int64_t)k * P.n + i] = make_float4(g[k].x, g[k].y, g[k].z, g[k].w);
+            if (rem == 0 || it + 1 >= fastRun) {
+              F.remaining[j] = rem;
+              __threadfence_block();  // another warp may pick this env up within this phase
+              if (rem > 0) ringPush(F.fastRing, &F.fastTail, j);
+              else atomicAdd(&F.doneCount, 1);
+              break;
+            }
+            groupsToEnv(g, e);
+          }
+        }
+        __syncwarp();
+      }
+      // A warp that found the ring empty may leave while another one is still about to re-queue envs; those are picked
+      // up in the next fast phase (after this block's general rounds), which keeps the phases strictly alternating.
+      __syncthreads();
+      if (P.phaseClk && lane == 0) {  // diagnostics (hk_debug_phase_cycles): fast batches, fast-phase cycles
+        atomicAdd(&P.phaseClk[4], (unsigned long long)batches);
+        if (threadIdx.x == 0) {
+          atomicAdd(&P.phaseClk[5], 1ull);
+          atomicAdd(&P.phaseClk[6], (unsigned long long)(clock64() - tf0));
+        }
+      }
+      if (F.doneCount >= m) break;
+      // ---- general phase: rounds of one general tick until nothing is filed ----
+      for (;;) {
+        const long long tr0 = clock64();
+        if (threadIdx.x == 0) {
+          int w = 0;
+#pragma unroll
+          for (int q = 0; q < Q_CLASSES; ++q) {
+            int avail = (int)(F.genTail[q] - F.genHead[q]);
+            while (avail > 0 && w < nwarps) {
+              const int cnt = avail < 32 ? avail : 32;
+              F.asgClass[w] = q;
+              F.asgStart[w] = (int)F.genHead[q];
+              F.asgCount[w] = cnt;
+              F.genHead[q] += (unsigned)cnt;
+              avail -= cnt;
+              ++w;
+            }
+          }
+          F.roundActive = w;
+          for (; w < nwarps; ++w) F.asgCount[w] = 0;
+        }
+        __syncthreads();
+        if (!F.roundActive) break;
+        const int envWarps = F.roundActive;
+        const int cnt = F.asgCount[wib], cls = F.asgClass[wib];
+        const bool valid = lane < cnt;
+        int j = 0;
+        if (valid) j = ringTake(F.genRing[cls], (unsigned)F.asgStart[wib] + (unsigned)lane);
+        const int64_t i = lo + j;
+        bool need = false;
+        GenStamps gs;
+        TickStats st;
+        generalTick<1, false>(P, io, S, sRaw, valid, i, cls, cnt > 0, (int64_t)wib, 1, phaseSync, envWarps, (int)blockDim.x,
+                              valid && F.remaining[j] == 1 && io.obs != nullptr, st, need, gs, &sSlowUnit, sFin);
+        if (valid) {
+          const int rem = --F.remaining[j];
+          if (rem > 0) ringPush(F.fastRing, &F.fastTail, j);
+          else atomicAdd(&F.doneCount, 1);
+        }
+        __syncthreads();
+        if (P.phaseClk) {  // diagnostics: rounds, their filled lanes, cycles in rounds
+          if (lane == 0 && cnt > 0) atomicAdd(&P.phaseClk[1], (unsigned long long)cnt);
+          if (threadIdx.x == 0) {
+            atomicAdd(&P.phaseClk[0], 1ull);
+            atomicAdd(&P.phaseClk[2], (unsigned long long)(clock64() - tr0));
+          }
+        }
+      }
+      if (F.doneCount >= m) break;
+    }
+    __syncthreads();
+  }
+  flushStats(statsRow(P.stats), stFast);
 }
 
 __global__ void __launch_bounds__(kBlock) k_get_obs(KParams P, float* obs, float* obs2) {
@@ -895,6 +1112,10 @@ struct hk_env {
   float* actBuf;
   uint32_t* trace;
   const uint8_t* pol2v = nullptr;  // hk_set_opponent_policies
+  bool fused = false;     // HK_FUSED=1: hk_rollout = ONE launch of k_rollout_fused instead of K x the per-tick cascade (measured
+                          // slower on B200: profiles/README.md, fused rollout)
+  int fusedFastRun = 4;   // HK_FUSED_FAST_RUN: consecutive fast ticks a lane takes with its state in registers before it is re-queued
+  int sms = 148;
   int tiers;  // HK_TIERS=2 (default): fast + unlimited general tier; 3: fast + budgeted + unlimited
   bool mono;  // HK_MONO=1: single general kernel per tick (the round-1 baseline, kept for A/B measurements)
   KParams params() const {
@@ -1001,6 +1222,7 @@ struct hk_env {
     cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
     cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
     cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 3));
+    cudaFuncSetAttribute(k_rollout_fused, cudaFuncAttributePreferredSharedMemoryCarveout, pct(rawBytes(kSlowBlock) + stat + sizeof(FusedShared)));
   }
   // Per-kernel timing (hk_kernel_timing): CUDA events recorded on the launching stream around every kernel of a tick,
   // kTimedSteps ticks deep; off by default (an event record is not part of a plain hk_step).
@@ -1033,6 +1255,12 @@ struct hk_env {
 };
 
 static bool validPolicy(int p) { return p >= HK_POLICY_EXTERNAL && p <= HK_POLICY_ZERO; }
+
+__global__ void k_sum_stats(const double* rows, double* out) {  // <<<1, HK_STATS_DIM>>>
+  double s = 0.0;
+  for (int r = 0; r < kStatsRows; ++r) s += rows[HK_STATS_DIM * r + threadIdx.x];
+  out[threadIdx.x] = s;
+}
 
 __global__ void k_check_codes(const uint8_t* codes, int64_t n, int* bad) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1110,6 +1338,9 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     cudaFuncAttributes fa;
     if (cudaFuncGetAttributes(&fa, k_general<1>) == cudaSuccess) h->staticSmem = fa.sharedSizeBytes;
     if (cudaFuncGetAttributes(&fa, k_fast<4>) == cudaSuccess) h->fastSmem = fa.sharedSizeBytes;
+    h->sms = sms;
+    if (const char* f = getenv("HK_FUSED")) h->fused = f[0] != '0';
+    if (const char* g = getenv("HK_FUSED_FAST_RUN")) h->fusedFastRun = std::max(1, atoi(g));
     h->targetBlocks = sms;  // one general-tier block per SM in a single wave (measured: 148 > 140 > 132 on a 148-SM B200)
     h->shapeTier1();
     h->launches = h->mono ? 1 : 2 + (h->touch ? 1 : 0) + (h->tiers == 3 ? 1 : 0);
@@ -1120,9 +1351,10 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   cudaError_t err = cudaMemcpyToSymbol(c_scene, &S, sizeof(Scene));
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_general<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_rollout_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->cache, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
-  if (err == cudaSuccess) err = cudaMalloc(&h->stats, sizeof(double) * HK_STATS_DIM);
+  if (err == cudaSuccess) err = cudaMalloc(&h->stats, sizeof(double) * HK_STATS_DIM * (kStatsRows + 1));  // rows + their sum
   if (err == cudaSuccess) err = cudaMalloc(&h->queue, sizeof(int32_t) * 5 * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 8);
@@ -1131,7 +1363,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 8);
   if (err == cudaSuccess && getenv("HK_LANE_TRACE")) err = cudaMalloc(&h->trace, sizeof(uint32_t) * (20 * ((size_t)n_envs / 32 + 8) + 2 * (size_t)n_envs));
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
-  if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM);
+  if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM * (kStatsRows + 1));
   if (err == cudaSuccess) {
     k_create<<<h->grid(), kBlock>>>(h->params());
     err = cudaGetLastError();
@@ -1270,6 +1502,16 @@ int hk_rollout(hk_env* h, int k_steps, int p1_policy, int p2_policy, float* obs_
   if (h->mono) {  // K ticks fused in one launch, state in registers between ticks (the round-1 baseline kernel)
     io.write = 1;
     k_rollout<<<h->grid(), kBlock, 0, (cudaStream_t)stream>>>(h->params(), io, k_steps);
+  } else if (h->fused) {  // K ticks in ONE launch without a per-tick join: fast envs run ahead, slow ones are re-queued
+    io.actBuf = h->actBuf;
+    io.write = obs_dev ? 1 : 0;
+    KParams P = h->params();
+    P.trace = nullptr;
+    int64_t chunk = (h->n + h->sms - 1) / h->sms;
+    if (chunk > kFusedChunk) chunk = kFusedChunk;
+    const int64_t nChunks = (h->n + chunk - 1) / chunk;
+    k_rollout_fused<<<(unsigned)std::min<int64_t>(nChunks, h->sms), kSlowBlock, rawBytes(kSlowBlock), (cudaStream_t)stream>>>(
+        P, io, k_steps, h->phaseSync, (int)chunk, (int)nChunks, h->fusedFastRun);
   } else {        // K ticks of the kernel cascade back to back; only the last tick writes its observation
     io.actBuf = h->actBuf;
     for (int s = 0; s < k_steps; ++s) {
@@ -1324,7 +1566,9 @@ int hk_set_obs_state(hk_env* h, const float* obs18_dev, void* stream) {
 int hk_get_stats(hk_env* h, double* out_host, void* stream) {
   if (!h || !out_host) return fail(HK_E_INVALID, "hk_get_stats: NULL argument");
   DeviceGuard guard(h->device);
-  HK_CUDA(cudaMemcpyAsync(out_host, h->stats, sizeof(double) * HK_STATS_DIM, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  double* sum = h->stats + HK_STATS_DIM * kStatsRows;
+  k_sum_stats<<<1, HK_STATS_DIM, 0, (cudaStream_t)stream>>>(h->stats, sum);
+  HK_CUDA(cudaMemcpyAsync(out_host, sum, sizeof(double) * HK_STATS_DIM, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   HK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return HK_OK;
 }
@@ -1332,14 +1576,15 @@ int hk_get_stats(hk_env* h, double* out_host, void* stream) {
 int hk_clear_stats(hk_env* h, void* stream) {
   if (!h) return fail(HK_E_INVALID, "hk_clear_stats: NULL handle");
   DeviceGuard guard(h->device);
-  HK_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(double) * HK_STATS_DIM, (cudaStream_t)stream));
+  HK_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(double) * HK_STATS_DIM * (kStatsRows + 1), (cudaStream_t)stream));
   return HK_OK;
 }
 
 int hk_copy_stats(hk_env* h, double* dst_dev, void* stream) {
   if (!h || !dst_dev) return fail(HK_E_INVALID, "hk_copy_stats: NULL argument");
   DeviceGuard guard(h->device);
-  HK_CUDA(cudaMemcpyAsync(dst_dev, h->stats, sizeof(double) * HK_STATS_DIM, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  k_sum_stats<<<1, HK_STATS_DIM, 0, (cudaStream_t)stream>>>(h->stats, dst_dev);
+  HK_CUDA(cudaGetLastError());
   return HK_OK;
 }
 
@@ -1398,7 +1643,11 @@ int hk_kernel_times(hk_env* h, double* out_ms4, int64_t* steps_out) {
 
 int hk_stats_device_ptr(hk_env* h, double** out_dev) {
   if (!h || !out_dev) return fail(HK_E_INVALID, "hk_stats_device_ptr: NULL argument");
-  *out_dev = h->stats;
+  DeviceGuard guard(h->device);
+  double* sum = h->stats + HK_STATS_DIM * kStatsRows;  // refreshed here (legacy default stream); stable address
+  k_sum_stats<<<1, HK_STATS_DIM>>>(h->stats, sum);
+  HK_CUDA(cudaGetLastError());
+  *out_dev = sum;
   return HK_OK;
 }
 

@@ -162,7 +162,8 @@ int hk_set_obs_state(hk_env* env, const float* obs18_dev, void* stream);
  * 15 reserved.  Synchronises `stream`. */
 int hk_get_stats(hk_env* env, double* out_host, void* stream);
 int hk_clear_stats(hk_env* env, void* stream);
-/* Device pointer to the HK_STATS_DIM accumulators (f64), for an NCCL all-reduce without a host hop. */
+/* Device pointer to HK_STATS_DIM doubles holding the accumulators as of this call (summed on the legacy default stream
+ * from the library's replicated per-block rows), for an NCCL all-reduce without a host hop. */
 int hk_stats_device_ptr(hk_env* env, double** out_dev);
 /* Device-to-device copy of the accumulators into a caller-owned f64[HK_STATS_DIM] buffer (async). */
 int hk_copy_stats(hk_env* env, double* dst_dev, void* stream);

@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--no-l2-flush", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--actor-impl", default="fused", choices=["fused", "torch"],
+                    help="config actor262k: the fused tcgen05 kernel (hk_actor_forward) or the fp32 torch module")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-zero-copy", action="store_true", help="kernels store outputs straight into mapped pinned memory")
     ap.add_argument("--rollout-k", type=int, default=64, help="ticks per hk_rollout call of the fused-rollout leg (0 = skip)")
@@ -266,7 +268,8 @@ def main():
     mode = hk.Mode[c["mode"]]
     actor = None
     if c["p1"] == "actor":
-        actor = hk.load_td3_actor(os.path.join(_ROOT, "tests", "golden", "td3_actors.npz"), device=dev, name="stage_3")
+        module = hk.load_td3_actor(os.path.join(_ROOT, "tests", "golden", "td3_actors.npz"), device=dev, name="stage_3")
+        actor = module if args.actor_impl == "torch" else hk.FusedActor(module, device=dev)
     env = hk.HockeyVecEnv(n, mode=mode, device=dev, seed=args.seed, env_id_offset=rank * n,
                           p1=None if actor is not None else c["p1"], p2=c["p2"])
     env.reset(one_starting=(torch.arange(n, device=dev) % 2).to(torch.int8))
@@ -446,7 +449,7 @@ def main():
             "e2e": e2e,
             "rollout": rollout,
             # kernels of this repo launched in the timed region: k_fast (+ k_touch) + the general tier(s) per tick
-            "gpu_launches": args.steps * env.launches_per_step(),
+            "gpu_launches": args.steps * (env.launches_per_step() + (1 if actor is not None and args.actor_impl == "fused" else 0)),
             "clocks": clocks,
             "kernel_ms_per_tick": {k: v / max(ksteps, 1) for k, v in ktimes.items()},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -468,7 +471,9 @@ def main():
                               "toi_events_per_step_preroll_tail": rates[-1], "preroll_ticks": preroll_ticks},
         }
         if actor is not None:
-            out["actor"] = {"ms_per_step": actor_ms / args.steps, "share_of_step": actor_ms / max(kernel_ms, 1e-9),
+            out["actor"] = {"impl": "fused tcgen05 kernel (hk_actor_forward: TF32 layer 1, bf16 layers 2-3, fp32 accumulation in TMEM)"
+                            if args.actor_impl == "fused" else "torch fp32 module (cuBLAS GEMMs + elementwise tanh)",
+                            "ms_per_step": actor_ms / args.steps, "share_of_step": actor_ms / max(kernel_ms, 1e-9),
                             "weights": "tests/golden/td3_actors.npz:stage_3 (pretrained/stage_3/models/td3_best.pt)",
                             "flops_per_env": 2 * (18 * 256 + 256 * 256 + 256 * 4)}
         if st[0] <= 0:

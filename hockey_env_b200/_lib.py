@@ -18,7 +18,7 @@ STEP_AUTORESET = 1
 
 EXPORTS = [
     "hk_create", "hk_destroy", "hk_num_envs", "hk_reset", "hk_reset_seeded", "hk_step", "hk_rollout", "hk_get_obs", "hk_get_info", "hk_get_state",
-    "hk_set_state", "hk_set_obs_state", "hk_set_opponent_policies", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_launches_per_step", "hk_debug_lane_trace", "hk_kernel_timing", "hk_kernel_times", "hk_last_error",
+    "hk_set_state", "hk_set_obs_state", "hk_set_opponent_policies", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_launches_per_step", "hk_debug_lane_trace", "hk_kernel_timing", "hk_kernel_times", "hk_actor_param_bytes", "hk_actor_forward", "hk_last_error",
     "hk_version",
 ]
 
@@ -71,6 +71,10 @@ def load():
     L.hk_kernel_timing.restype = i32
     L.hk_kernel_times.argtypes = [vp, vp, C.POINTER(i64)]
     L.hk_kernel_times.restype = i32
+    L.hk_actor_param_bytes.argtypes = []
+    L.hk_actor_param_bytes.restype = i32
+    L.hk_actor_forward.argtypes = [vp, vp, vp, i32, i64, i32, vp]
+    L.hk_actor_forward.restype = i32
     L.hk_launches_per_step.argtypes = [vp]
     L.hk_launches_per_step.restype = i32
     L.hk_get_state.argtypes = [vp, vp, vp]

@@ -46,6 +46,67 @@ def load_td3_actor(path, device="cuda:0", name=None):
     return actor.to(device).eval()
 
 
+class FusedActor:
+    """The same network as ONE fused sm_100a tensor-core kernel (csrc/hk_actor.cuh, hk_actor_forward): weights resident in
+    shared memory (layer 1 TF32, layers 2-3 bf16), fp32 accumulation in tensor memory, hidden activations never leave the SM.  Callable like the
+    module: obs [N,18] float32 CUDA tensor -> actions [N,4] (a persistent output buffer, overwritten by the next call;
+    pass `out=` to write into columns 0..3 of an existing [N,4] / [N,8] action tensor).  There is no fallback: without the
+    CUDA library or a GPU this raises."""
+
+    def __init__(self, actor, device="cuda:0"):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib = C, _lib
+        self.L = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda" or not torch.cuda.is_available():
+            raise _lib.HockeyLibraryError("FusedActor needs a CUDA device: the actor kernel has no CPU fallback")
+        sd = {k: v.detach().to("cpu", torch.float32) for k, v in actor.state_dict().items()}
+        if tuple(sd["fc1.weight"].shape) != (256, 18) or tuple(sd["fc2.weight"].shape) != (256, 256) or tuple(sd["fc3.weight"].shape) != (4, 256):
+            raise ValueError("FusedActor implements the reference architecture 18 -> 256 -> 256 -> 4")
+        self.params = self.pack(sd).to(self.device)
+        assert self.params.numel() == int(self.L.hk_actor_param_bytes())
+        self._out = None
+
+    @staticmethod
+    def _core_matrix_order(w, n_pad, k_pad, dtype):
+        """[N, K] float weight -> bytes in UMMA K-major core-matrix order (8-row x 16-byte core matrices, no swizzle):
+        with e = 16 / itemsize elements per 16-byte chunk, element (n, k) sits at
+        (k // e) * (n_pad * 16) + n * 16 + (k % e) * itemsize bytes.  dtype bfloat16, or float32 for the TF32 layer."""
+        full = torch.zeros((n_pad, k_pad), dtype=torch.float32)
+        full[:w.shape[0], :w.shape[1]] = w
+        e = 16 // torch.empty((), dtype=dtype).element_size()
+        return full.to(dtype).view(n_pad, k_pad // e, e).permute(1, 0, 2).contiguous().view(torch.uint8).flatten()
+
+    @classmethod
+    def pack(cls, sd):
+        b3 = torch.zeros(16, dtype=torch.float32)
+        b3[:4] = sd["fc3.bias"]
+        parts = [cls._core_matrix_order(sd["fc1.weight"], 256, 24, torch.float32),
+                 cls._core_matrix_order(sd["fc2.weight"], 256, 256, torch.bfloat16),
+                 cls._core_matrix_order(sd["fc3.weight"], 16, 256, torch.bfloat16),
+                 sd["fc1.bias"].contiguous().view(torch.uint8).flatten(),
+                 sd["fc2.bias"].contiguous().view(torch.uint8).flatten(), b3.view(torch.uint8).flatten()]
+        return torch.cat(parts).contiguous()
+
+    def __call__(self, obs, out=None):
+        if not (obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and obs.dim() == 2 and obs.shape[1] == 18):
+            raise ValueError("FusedActor expects a contiguous float32 CUDA tensor [N, 18]")
+        n = obs.shape[0]
+        if out is None:
+            if self._out is None or self._out.shape[0] != n:
+                self._out = torch.empty((n, 4), dtype=torch.float32, device=obs.device)
+            out = self._out
+        if not (out.is_cuda and out.dtype == torch.float32 and out.dim() == 2 and out.shape[0] == n and out.stride(1) == 1 and out.shape[1] >= 4):
+            raise ValueError("out must be a float32 CUDA tensor [N, >= 4] with unit column stride")
+        C = self._C
+        with torch.cuda.device(obs.device):
+            self._lib.check(self.L.hk_actor_forward(C.c_void_p(self.params.data_ptr()), C.c_void_p(obs.data_ptr()),
+                                                    C.c_void_p(out.data_ptr()), int(out.stride(0)), n, obs.device.index or 0,
+                                                    C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)))
+        return out[:, :4] if out.shape[1] != 4 else out
+
+
 @torch.no_grad()
 def actor_rollout(env, actor, steps, opponent_actor=None):
     """`steps` ticks of `env` (a HockeyVecEnv with p1 external) driven by `actor`; player 2 is the env's in-kernel

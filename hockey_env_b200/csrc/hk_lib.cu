@@ -17,6 +17,7 @@
 
 #include "../../include/hockey_b200.h"
 #include "hk_tick.cuh"
+#include "hk_actor.cuh"
 
 using namespace hk;
 
@@ -74,6 +75,7 @@ __device__ __forceinline__ void storeEnv(float4* __restrict__ core, int64_t n, i
 }
 
 __device__ __forceinline__ void flushInt(double* gstats, int slot, int v, int lane) {
+  if (!__any_sync(0xffffffffu, v != 0)) return;  // most statistics are zero for a whole warp in most ticks
   int s = __reduce_add_sync(0xffffffffu, v);
   if (lane == 0 && s != 0) atomicAdd(&gstats[slot], (double)s);
 }
@@ -1169,6 +1171,7 @@ struct hk_env {
     // automatic class-homogeneous block shape (k_general) with up to envWarps1 env warps per block
     if (tiers == 2 && !getenv("HK_ENV_WARPS") && targetBlocks > 0) {
       envWarps1 = n <= 40000 ? 4 : (n <= 100000 ? 8 : maxWarps);
+      if (const char* e = getenv("HK_AUTO_WARPS")) envWarps1 = std::min(maxWarps, std::max(1, atoi(e)));  // largest block of the automatic shape
       block1 = envWarps1 * 32;
       if (const char* e = getenv("HK_SLOW_BLOCK")) block1 = std::min(kSlowBlock, std::max(block1, atoi(e) / 32 * 32));
       classWarps1 = -targetBlocks;
@@ -1218,7 +1221,8 @@ struct hk_env {
     auto pct = [](size_t bytes) { return (int)std::min<size_t>(100, (bytes * 100 + 228 * 1024 - 1) / (228 * 1024)); };
     const size_t stat = staticSmem;
     const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
-    cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? 1 : perSm1)));
+    const int perSmAuto = std::max(1, (targetBlocks + sms - 1) / sms);  // automatic shape: blocks per SM the target asks for
+    cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)));
     cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
     cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
     cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 3));
@@ -1603,6 +1607,30 @@ int hk_debug_lane_trace(hk_env* h, uint32_t* out_host, int64_t n_words) {
   const int64_t have = 20 * (h->n / 32 + 8) + 2 * h->n;
   DeviceGuard guard(h->device);
   HK_CUDA(cudaMemcpy(out_host, h->trace, sizeof(uint32_t) * (size_t)(n_words < have ? n_words : have), cudaMemcpyDeviceToHost));
+  return HK_OK;
+}
+
+int hk_actor_param_bytes(void) { return hk_actor::kParamBytes; }
+
+int hk_actor_forward(const void* params_dev, const float* obs_dev, float* act_dev, int act_stride, int64_t n, int device, void* stream) {
+  if (!params_dev || !obs_dev || !act_dev) return fail(HK_E_INVALID, "hk_actor_forward: NULL argument");
+  if (n <= 0 || act_stride < hk_actor::kAct) return fail(HK_E_INVALID, "hk_actor_forward: n must be positive and act_stride >= 4");
+  if ((((uintptr_t)params_dev) & 15u) || (((uintptr_t)obs_dev) & 7u)) return fail(HK_E_INVALID, "hk_actor_forward: params need 16-byte, obs 8-byte alignment");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(HK_E_NODEVICE, "hk_actor_forward: no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= count) return fail(HK_E_INVALID, "hk_actor_forward: bad device index");
+  DeviceGuard guard(device);
+  static bool configured[64] = {false};
+  if (!configured[device & 63]) {
+    HK_CUDA(cudaFuncSetAttribute(hk_actor::k_actor_mlp, cudaFuncAttributeMaxDynamicSharedMemorySize, hk_actor::kSmemBytes));
+    configured[device & 63] = true;
+  }
+  int sms = 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 1) sms = 148;
+  const int64_t tiles = (n + hk_actor::kRows - 1) / hk_actor::kRows;
+  hk_actor::k_actor_mlp<<<(unsigned)std::min<int64_t>(tiles, sms), hk_actor::kThreads, hk_actor::kSmemBytes, (cudaStream_t)stream>>>(
+      (const unsigned char*)params_dev, obs_dev, act_dev, act_stride, (long long)n);
+  HK_CUDA(cudaGetLastError());
   return HK_OK;
 }
 

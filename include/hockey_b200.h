@@ -177,6 +177,16 @@ int hk_debug_lane_trace(hk_env* env, uint32_t* out_host, int64_t n_words);
 /* Kernels one hk_step launches on this handle (k_fast, k_touch, general tier(s)); for launch accounting. */
 int hk_launches_per_step(const hk_env* env);
 
+/* The reference's TD3 actor (ActorNetwork.forward, rl/td3/networks.py:17-20: 18 -> 256 -> 256 -> 4, tanh after every layer)
+ * as one fused tensor-core kernel (BASELINE config 5): act[i, 0..3] = actor(obs[i, 0..17]) for n rows.  params_dev: the
+ * hk_actor_param_bytes()-byte block laid out as csrc/hk_actor.cuh describes (bf16 weights in UMMA core-matrix order, f32
+ * biases; hockey_env_b200.actor.FusedActor packs it from a torch module).  obs_dev: f32 [n, 18] contiguous; act_dev: f32
+ * rows of act_stride >= 4 floats (e.g. the [n, 4] or [n, 8] action tensor of the next hk_step).  bf16 operands, fp32
+ * accumulation.  Enqueued on `stream`; graph-capturable. */
+int hk_actor_param_bytes(void);
+int hk_actor_forward(const void* params_dev, const float* obs_dev, float* act_dev, int act_stride, int64_t n, int device,
+                     void* stream);
+
 /* Measurement: per-kernel device times of the ticks that follow.  hk_kernel_timing(env, 1) makes every hk_step /
  * hk_rollout tick record CUDA events on the launching stream around each kernel of the cascade (up to 2048 ticks; not
  * graph-capturable while enabled); hk_kernel_times synchronises the device, returns the summed milliseconds of

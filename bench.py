@@ -240,7 +240,9 @@ def main():
     ap.add_argument("--actor-impl", default="fused", choices=["fused", "torch"],
                     help="config actor262k: the fused tcgen05 kernel (hk_actor_forward) or the fp32 torch module")
     ap.add_argument("--e2e-steps", type=int, default=100)
-    ap.add_argument("--e2e-zero-copy", action="store_true", help="kernels store outputs straight into mapped pinned memory")
+    ap.add_argument("--e2e-mode", default="copy", choices=["copy", "overlap", "zero_copy"],
+                    help="HockeyVecEnv.step_host mode: one D2H copy of the packed record after the tick (default), DMA of the fast "
+                         "tier's rows overlapped with the general tier, or zero-copy stores only")
     ap.add_argument("--rollout-k", type=int, default=64, help="ticks per hk_rollout call of the fused-rollout leg (0 = skip)")
     args = ap.parse_args()
 
@@ -395,12 +397,12 @@ def main():
         e2e_env.set_full_state(snap)
         host = e2e_env.host_buffers()
         for k in range(e2e_warm):
-            e2e_env.step_host(h_acts[k], host, zero_copy=args.e2e_zero_copy)
+            e2e_env.step_host(h_acts[k], host, mode=args.e2e_mode)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(e2e_steps):
-            e2e_env.step_host(h_acts[e2e_warm + k], host, zero_copy=args.e2e_zero_copy)  # H2D, tick, D2H, stream sync
+            e2e_env.step_host(h_acts[e2e_warm + k], host, mode=args.e2e_mode)  # H2D, tick, D2H, stream sync
         e1.record()
         barrier()
         same = bool(torch.equal(host["host"]["obs"], obs.cpu()))  # the replay ended where the recording pass ended
@@ -412,8 +414,11 @@ def main():
                "steps": e2e_steps, "ms_per_step": float(t.item()) / e2e_steps, "replay_matches_recording": same,
                "note": "HockeyVecEnv.step_host: player-1 actions from pinned host memory (recorded closed-loop from the same "
                        f"steady state: p1 = {c['p1']}), obs/reward/done/info "
-                       + ("stored by the kernels straight into" if args.e2e_zero_copy else "packed and copied with ONE D2H copy to")
-                       + f" pinned host memory, host sync every tick; player 2 = in-kernel {p2}"}
+                       + {"overlap": "reach pinned host memory by a DMA of the fast tier's rows that overlaps the general tier plus the "
+                                     "general tier's own stores into the mapped record (hk_step_host)",
+                          "copy": "are packed and copied with ONE D2H copy to pinned host memory",
+                          "zero_copy": "are stored by the kernels straight into mapped pinned host memory"}[args.e2e_mode]
+                       + f", host sync every tick; player 2 = in-kernel {p2}", "mode": args.e2e_mode}
         e2e_env.close()
 
     # ---- end-of-run statistics: the only collective on this path (NCCL all-reduce of 16 doubles)

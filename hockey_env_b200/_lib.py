@@ -17,7 +17,7 @@ POLICY_EXTERNAL, POLICY_BASIC_WEAK, POLICY_BASIC_STRONG, POLICY_RANDOM, POLICY_Z
 STEP_AUTORESET = 1
 
 EXPORTS = [
-    "hk_create", "hk_destroy", "hk_num_envs", "hk_reset", "hk_reset_seeded", "hk_step", "hk_rollout", "hk_get_obs", "hk_get_info", "hk_get_state",
+    "hk_create", "hk_destroy", "hk_num_envs", "hk_reset", "hk_reset_seeded", "hk_step", "hk_step_host", "hk_host_record_bytes", "hk_rollout", "hk_get_obs", "hk_get_info", "hk_get_state",
     "hk_set_state", "hk_set_obs_state", "hk_set_opponent_policies", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_launches_per_step", "hk_debug_lane_trace", "hk_kernel_timing", "hk_kernel_times", "hk_actor_param_bytes", "hk_actor_forward", "hk_last_error",
     "hk_version",
 ]
@@ -53,6 +53,10 @@ def load():
     L.hk_reset_seeded.restype = i32
     L.hk_step.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hk_step.restype = i32
+    L.hk_step_host.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
+    L.hk_step_host.restype = i32
+    L.hk_host_record_bytes.argtypes = [i64, i32, C.POINTER(i64)]
+    L.hk_host_record_bytes.restype = i64
     L.hk_set_opponent_policies.argtypes = [vp, vp]
     L.hk_set_opponent_policies.restype = i32
     L.hk_rollout.argtypes = [vp, i32, i32, i32, vp, vp]

@@ -641,6 +641,11 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
     if (threadIdx.x < 4) sFin[threadIdx.x] = 0;
     teamSync<TEAM>(nthr);
   }
+  if (io.waitFlag) {  // hk_step_host: this tick's rows of the fast tier are being copied into the host record the outputs go to
+    if (threadIdx.x == 0)
+      while (*((volatile const uint32_t*)io.waitFlag) != io.waitValue) __nanosleep(200);
+    teamSync<TEAM>(nthr);
+  }
   const long long tf0 = clock64();
   long long tf1 = tf0, tf2 = tf0;
   if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
@@ -1236,7 +1241,14 @@ struct hk_env {
   void stamp(int k, cudaStream_t stream) const {
     if (events && timedSteps < kTimedSteps) cudaEventRecord(events[timedSteps * kEventsPerStep + k], stream);
   }
-  void launchCascade(const StepIO& io, cudaStream_t stream) const {
+  // host-record path (hk_step_host): side stream for the DMA that overlaps the general tier
+  cudaStream_t sideStream = nullptr;
+  cudaEvent_t evTiers = nullptr, evCopy = nullptr;
+  uint32_t* flagDev = nullptr;
+  uint32_t* seqHost = nullptr;  // pinned table seq[k] = k: the source of the 4-byte "copy done" flag writes
+  uint32_t hostTick = 0;
+  void launchCascade(const StepIO& io, cudaStream_t stream, const StepIO* ioGeneral = nullptr, void (*between)(const hk_env*, cudaStream_t, void*) = nullptr,
+                     void* betweenArg = nullptr) const {
     if (g_shapedFor != shapeKey()) {
       shapeSharedMemory();
       g_shapedFor = shapeKey();
@@ -1248,11 +1260,13 @@ struct hk_env {
     stamp(1, stream);
     if (touch) k_touch<<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     stamp(2, stream);
+    if (between) between(this, stream, betweenArg);
+    const StepIO& iog = ioGeneral ? *ioGeneral : io;
     const int b2 = blockTier2(), w2 = b2 / 32;
     k_general<1><<<gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(
-        params(), io, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
+        params(), iog, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
     stamp(3, stream);
-    if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), io, 1, lanes2, 0, phaseSync, w2, 0);
+    if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), iog, 1, lanes2, 0, phaseSync, w2, 0);
     stamp(4, stream);
     if (events && timedSteps < kTimedSteps) ++timedSteps;
   }
@@ -1405,6 +1419,13 @@ int hk_destroy(hk_env* h) {
     for (int k = 0; k < hk_env::kTimedSteps * hk_env::kEventsPerStep; ++k) cudaEventDestroy(h->events[k]);
     delete[] h->events;
   }
+  if (h->sideStream) {
+    cudaStreamDestroy(h->sideStream);
+    cudaEventDestroy(h->evTiers);
+    cudaEventDestroy(h->evCopy);
+    cudaFree(h->flagDev);
+    cudaFreeHost(h->seqHost);
+  }
   delete h;
   return HK_OK;
 }
@@ -1461,6 +1482,8 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
   io.final_obs = final_obs_dev;
   io.write = 1;
   io.actBuf = nullptr;
+  io.waitFlag = nullptr;
+  io.waitValue = 0;
   // k_fast writes a warp's 32 rows with 128-bit stores when the row tensors are 16-byte aligned (torch tensors are)
   io.stageRows = (((uintptr_t)obs_dev | (uintptr_t)final_obs_dev) & 15u) == 0 ? 1 : 0;
   if (h->mono) {
@@ -1468,6 +1491,105 @@ int hk_step(hk_env* h, const float* action_dev, int action_stride, int p1_policy
   } else {
     io.actBuf = h->actBuf;
     h->launchCascade(io, (cudaStream_t)stream);
+  }
+  HK_CUDA(cudaGetLastError());
+  return HK_OK;
+}
+
+// ---- host-record stepping ------------------------------------------------------------------------------------------------
+// packed record: obs [n,18] f32 | reward [n] f32 | info [n,4] f32 | done [n] u8 (| final_obs [n,18] f32), sections 256-byte aligned
+static int64_t recordLayout(int64_t n, int with_final_obs, int64_t off[5]) {
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  int64_t t = 0;
+  off[0] = t; t += up(72 * n);
+  off[1] = t; t += up(4 * n);
+  off[2] = t; t += up(16 * n);
+  off[3] = t; t += up(n);
+  off[4] = t;
+  if (with_final_obs) t += up(72 * n);
+  return t;
+}
+int64_t hk_host_record_bytes(int64_t n_envs, int with_final_obs, int64_t* offsets5) {
+  int64_t off[5];
+  const int64_t t = recordLayout(n_envs, with_final_obs, off);
+  if (offsets5) for (int k = 0; k < 5; ++k) offsets5[k] = off[k];
+  return t;
+}
+static StepIO recordIO(const StepIO& base, uint8_t* rec, const int64_t off[5], int with_final_obs) {
+  StepIO io = base;
+  io.obs = reinterpret_cast<float*>(rec + off[0]);
+  io.reward = reinterpret_cast<float*>(rec + off[1]);
+  io.info = reinterpret_cast<float*>(rec + off[2]);
+  io.done = rec + off[3];
+  io.final_obs = with_final_obs ? reinterpret_cast<float*>(rec + off[4]) : nullptr;
+  io.obs2 = io.reward2 = io.info2 = nullptr;
+  return io;
+}
+struct HostCopyArgs {
+  uint8_t* recDev;
+  uint8_t* recHost;
+  int64_t bytes;
+};
+static void copyFastRows(const hk_env* h, cudaStream_t stream, void* argp) {
+  // The fast (and touch) tier's rows are complete: a copy engine moves the device record to the host while the general
+  // tier runs; a 4-byte DMA write behind it raises the flag the general tier waits for before ITS rows go to the host.
+  const HostCopyArgs* a = static_cast<const HostCopyArgs*>(argp);
+  cudaEventRecord(h->evTiers, stream);
+  cudaStreamWaitEvent(h->sideStream, h->evTiers, 0);
+  cudaMemcpyAsync(a->recHost, a->recDev, (size_t)a->bytes, cudaMemcpyDeviceToHost, h->sideStream);
+  cudaMemcpyAsync(h->flagDev, h->seqHost + (h->hostTick & 0xFFFFu), sizeof(uint32_t), cudaMemcpyHostToDevice, h->sideStream);
+  cudaEventRecord(h->evCopy, h->sideStream);
+}
+
+int hk_step_host(hk_env* h, const float* action_host, int action_stride, int p1_policy, int p2_policy, int flags, float* action_dev,
+                 uint8_t* record_dev, uint8_t* record_host, int with_final_obs, void* stream) {
+  if (!h) return fail(HK_E_INVALID, "hk_step_host: NULL handle");
+  if (!record_dev || !record_host) return fail(HK_E_INVALID, "hk_step_host: record_dev and record_host are required");
+  const bool perEnv = p2_policy == HK_POLICY_PER_ENV;
+  if (!validPolicy(p1_policy) || !(validPolicy(p2_policy) || perEnv)) return fail(HK_E_INVALID, "hk_step_host: invalid policy id");
+  if (perEnv && !h->pol2v) return fail(HK_E_INVALID, "hk_step_host: HK_POLICY_PER_ENV without hk_set_opponent_policies");
+  const bool ext = p1_policy == HK_POLICY_EXTERNAL || p2_policy == HK_POLICY_EXTERNAL || perEnv;
+  if (ext && (!action_host || !action_dev)) return fail(HK_E_INVALID, "hk_step_host: action buffers are NULL but a policy is EXTERNAL");
+  if (ext && (action_stride < 4 || ((p2_policy == HK_POLICY_EXTERNAL || perEnv) && action_stride < 8)))
+    return fail(HK_E_INVALID, "hk_step_host: action_stride too small for the EXTERNAL policies");
+  if ((((uintptr_t)record_dev | (uintptr_t)record_host) & 15u) != 0) return fail(HK_E_INVALID, "hk_step_host: records must be 16-byte aligned");
+  DeviceGuard guard(h->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->sideStream) {
+    HK_CUDA(cudaStreamCreateWithFlags(&h->sideStream, cudaStreamNonBlocking));
+    HK_CUDA(cudaEventCreateWithFlags(&h->evTiers, cudaEventDisableTiming));
+    HK_CUDA(cudaEventCreateWithFlags(&h->evCopy, cudaEventDisableTiming));
+    HK_CUDA(cudaMalloc(&h->flagDev, sizeof(uint32_t)));
+    HK_CUDA(cudaMemset(h->flagDev, 0xFF, sizeof(uint32_t)));
+    HK_CUDA(cudaMallocHost(&h->seqHost, sizeof(uint32_t) * 65536));
+    for (uint32_t k = 0; k < 65536; ++k) h->seqHost[k] = k;
+  }
+  int64_t off[5];
+  const int64_t bytes = recordLayout(h->n, with_final_obs, off);
+  if (ext) HK_CUDA(cudaMemcpyAsync(action_dev, action_host, sizeof(float) * (size_t)action_stride * (size_t)h->n, cudaMemcpyHostToDevice, st));
+  StepIO io;
+  std::memset(&io, 0, sizeof(io));
+  io.action = ext ? action_dev : nullptr;
+  io.stride = action_stride;
+  io.pol1 = p1_policy;
+  io.pol2 = perEnv ? HK_POLICY_ZERO : p2_policy;
+  io.pol2v = perEnv ? h->pol2v : nullptr;
+  io.flags = flags;
+  io.write = 1;
+  StepIO ioDev = recordIO(io, record_dev, off, with_final_obs);
+  ioDev.stageRows = 1;
+  if (h->mono) {  // single-kernel baseline: device record, then one copy
+    k_step<<<h->grid(), kBlock, 0, st>>>(h->params(), ioDev);
+    HK_CUDA(cudaMemcpyAsync(record_host, record_dev, (size_t)bytes, cudaMemcpyDeviceToHost, st));
+  } else {
+    ioDev.actBuf = h->actBuf;
+    ++h->hostTick;
+    StepIO ioHost = recordIO(ioDev, record_host, off, with_final_obs);  // the general tier stores straight into the mapped host record
+    ioHost.waitFlag = h->flagDev;
+    ioHost.waitValue = h->hostTick & 0xFFFFu;
+    HostCopyArgs args{record_dev, record_host, bytes};
+    h->launchCascade(ioDev, st, &ioHost, copyFastRows, &args);
+    HK_CUDA(cudaStreamWaitEvent(st, h->evCopy, 0));  // whoever waits on `stream` also waits for the DMA
   }
   HK_CUDA(cudaGetLastError());
   return HK_OK;

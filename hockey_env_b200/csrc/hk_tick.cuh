@@ -23,6 +23,8 @@ struct StepIO {
   int write;         // 0: suppress all per-tick outputs (inner ticks of hk_rollout)
   float* actBuf;     // [n,8] scratch: clipped actions k_fast computed for the envs it hands to the general tiers
   int stageRows;     // k_fast: write obs / final_obs rows warp-cooperatively (needs 16-byte aligned row tensors)
+  const uint32_t* waitFlag;  // general tier (hk_step_host): outputs may be written once *waitFlag == waitValue
+  uint32_t waitValue;        //   (the DMA of the fast tier's rows into the same host record has finished)
 };
 
 HK_HD int pol2Of(const StepIO& io, size_t i) { return io.pol2v ? (int)io.pol2v[i] : io.pol2; }

@@ -127,6 +127,19 @@ int hk_step(hk_env* env, const float* action_dev, int action_stride, int p1_poli
             float* obs_dev, float* obs2_dev, float* reward_dev, float* reward2_dev, uint8_t* done_dev,
             float* info_dev, float* info2_dev, float* final_obs_dev, void* stream);
 
+/* One tick for a HOST-side agent (the reference's own calling pattern: numpy in, numpy out).  action_host: PINNED host
+ * memory, f32 [n, action_stride] (nullable when no policy is EXTERNAL); record_host: PINNED host memory of
+ * hk_host_record_bytes(n, with_final_obs, offsets) bytes laid out as obs [n,18] f32 | reward [n] f32 | info [n,4] f32 |
+ * done [n] u8 (| final_obs [n,18] f32) at offsets[0..4]; action_dev / record_dev: caller-owned device scratch of the same
+ * sizes.  The actions are copied in on `stream`, the fast tier writes its rows to the device record, a copy engine moves
+ * that record to the host on an internal side stream WHILE the general tier runs, and the general tier stores its own
+ * rows straight into the mapped host record once that copy has landed -- so almost all of the device-to-host traffic
+ * overlaps the tick.  Everything is ordered into `stream`: after a synchronize on it the host record holds the tick's
+ * results.  Not CUDA-graph capturable. */
+int64_t hk_host_record_bytes(int64_t n_envs, int with_final_obs, int64_t* offsets5);
+int hk_step_host(hk_env* env, const float* action_host, int action_stride, int p1_policy, int p2_policy, int flags,
+                 float* action_dev, uint8_t* record_dev, uint8_t* record_host, int with_final_obs, void* stream);
+
 /* Per-env opponent selection (the reference draws an opponent per episode from a pool: weak / strong
  * BasicOpponent or a self-play snapshot, rl/training/opponent_manager.py:62-91, rl/training/self_play.py:7-68).
  * codes_dev: n_envs bytes of HK_POLICY_EXTERNAL..HK_POLICY_ZERO, caller-owned device memory that must stay valid

@@ -66,7 +66,7 @@ void hs_step(void* h, const float* action, int stride, int pol1, int pol2, int f
              float* reward2, uint8_t* done, float* info, float* info2, float* final_obs) {
   HostBatch* b = (HostBatch*)h;
   StepIO io; io.action = action; io.stride = stride; io.pol1 = pol1; io.pol2 = pol2; io.pol2v = nullptr; io.flags = flags; io.obs = obs; io.obs2 = obs2;
-  io.reward = reward; io.reward2 = reward2; io.done = done; io.info = info; io.info2 = info2; io.final_obs = final_obs; io.write = 1; io.actBuf = nullptr; io.stageRows = 0;
+  io.reward = reward; io.reward2 = reward2; io.done = done; io.info = info; io.info2 = info2; io.final_obs = final_obs; io.write = 1; io.actBuf = nullptr; io.stageRows = 0; io.waitFlag = nullptr; io.waitValue = 0;
   for (int64_t i = 0; i < b->n; ++i) {
     // round-trip through the HBM group layout exactly as the kernel does
     F4 g[CORE_GROUPS];

@@ -18,7 +18,7 @@ STEP_AUTORESET = 1
 
 EXPORTS = [
     "hk_create", "hk_destroy", "hk_num_envs", "hk_reset", "hk_reset_seeded", "hk_step", "hk_step_host", "hk_host_record_bytes", "hk_rollout", "hk_get_obs", "hk_get_info", "hk_get_state",
-    "hk_set_state", "hk_set_obs_state", "hk_set_opponent_policies", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_launches_per_step", "hk_debug_lane_trace", "hk_kernel_timing", "hk_kernel_times", "hk_actor_param_bytes", "hk_actor_forward", "hk_last_error",
+    "hk_set_state", "hk_set_obs_state", "hk_set_opponent_policies", "hk_get_stats", "hk_clear_stats", "hk_stats_device_ptr", "hk_copy_stats", "hk_debug_phase_cycles", "hk_debug_finish_cycles", "hk_launches_per_step", "hk_debug_lane_trace", "hk_kernel_timing", "hk_kernel_times", "hk_actor_param_bytes", "hk_actor_forward", "hk_last_error",
     "hk_version",
 ]
 
@@ -69,6 +69,8 @@ def load():
     L.hk_copy_stats.restype = i32
     L.hk_debug_phase_cycles.argtypes = [vp, vp]
     L.hk_debug_phase_cycles.restype = i32
+    L.hk_debug_finish_cycles.argtypes = [vp, vp]
+    L.hk_debug_finish_cycles.restype = i32
     L.hk_debug_lane_trace.argtypes = [vp, vp, C.c_int64]
     L.hk_debug_lane_trace.restype = i32
     L.hk_kernel_timing.argtypes = [vp, i32]

@@ -316,7 +316,7 @@ __host__ __device__ constexpr size_t rawBytes(int envLanes) {  // dynamic shared
   return solve > toi ? solve : toi;
 }
 struct GenStamps {  // diagnostics: clock stamps of the phase boundaries of one general tick
-  long long tc0, tc1, tc2, tc3, stampB, stampV, stampT;
+  long long tc0, tc1, tc2, tc3, stampB, stampV, stampT, tf0, tfCommit, tfFinish, tfStore, tfFlush;
 };
 // barrier among the threads that walk a general tick together: the whole block (k_general), or the general team of the
 // fused rollout kernel (its first `nthr` threads; the other warps of that block run fast ticks meanwhile)
@@ -648,6 +648,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
   }
   const long long tf0 = clock64();
   long long tf1 = tf0, tf2 = tf0;
+  gs.tf0 = tf0;
   if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
     if (!e.aborted) {
       worldStepFinish(cache, e);
@@ -661,6 +662,10 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
       need = true;
     }
   }
+  __syncwarp();
+  gs.tfCommit = tf1;
+  gs.tfFinish = tf2;
+  gs.tfStore = clock64();
   if (__any_sync(0xffffffffu, valid)) {
     if (TIER == 1 && !TEAM) {
       const unsigned m = __ballot_sync(0xffffffffu, need);
@@ -674,6 +679,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
     flushInt(statsRow(P.stats), 14, st.steps, lane);  // env-ticks completed by the general tiers (units of work per launch)
     flushStats(statsRow(P.stats), st);
   }
+  gs.tfFlush = clock64();
   if (P.trace && valid) {
     atomicMax(&sFin[0], (unsigned)(tf1 - tf0));
     atomicMax(&sFin[1], (unsigned)(tf2 - tf1));
@@ -810,6 +816,14 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
         w[13] = sFin[1];
         w[14] = sFin[2];
         w[15] = sFin[3];
+      }
+      if (!P.trace && TIER == 1) {  // finish-phase split as warp 0 saw it: tc3->start, commit, tickFinish, store | flush, final barrier
+        atomicAdd(&P.phaseClk[8], (unsigned long long)(gs.tf0 - tc3));
+        atomicAdd(&P.phaseClk[9], (unsigned long long)(gs.tfCommit - gs.tf0));
+        atomicAdd(&P.phaseClk[10], (unsigned long long)(gs.tfFinish - gs.tfCommit));
+        atomicAdd(&P.phaseClk[11], (unsigned long long)(gs.tfStore - gs.tfFinish));
+        atomicAdd(&P.phaseClk[12], (unsigned long long)(gs.tfFlush - gs.tfStore));
+        atomicAdd(&P.phaseClk[13], (unsigned long long)(tc4 - gs.tfFlush));
       }
       unsigned long long* pc = P.phaseClk + 4 * (TIER - 1);
       atomicAdd(&pc[0], (unsigned long long)(tc1 - tc0));
@@ -1377,8 +1391,8 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   if (err == cudaSuccess) err = cudaMalloc(&h->qctl, sizeof(uint32_t) * 8);
   if (err == cudaSuccess) err = cudaMemset(h->qctl, 0, sizeof(uint32_t) * 8);
   if (err == cudaSuccess) err = cudaMalloc(&h->actBuf, sizeof(float) * 8 * (size_t)n_envs);
-  if (err == cudaSuccess) err = cudaMalloc(&h->phaseClk, sizeof(unsigned long long) * 8);
-  if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 8);
+  if (err == cudaSuccess) err = cudaMalloc(&h->phaseClk, sizeof(unsigned long long) * 16);
+  if (err == cudaSuccess) err = cudaMemset(h->phaseClk, 0, sizeof(unsigned long long) * 16);
   if (err == cudaSuccess && getenv("HK_LANE_TRACE")) err = cudaMalloc(&h->trace, sizeof(uint32_t) * (20 * ((size_t)n_envs / 32 + 8) + 2 * (size_t)n_envs));
   if (err == cudaSuccess) err = cudaMemset(h->cache, 0, sizeof(uint32_t) * 6 * N_PAIRS * (size_t)n_envs);
   if (err == cudaSuccess) err = cudaMemset(h->stats, 0, sizeof(double) * HK_STATS_DIM * (kStatsRows + 1));
@@ -1717,9 +1731,18 @@ int hk_copy_stats(hk_env* h, double* dst_dev, void* stream) {
 int hk_debug_phase_cycles(hk_env* h, double* out_host8) {
   if (!h || !out_host8) return fail(HK_E_INVALID, "hk_debug_phase_cycles: NULL argument");
   DeviceGuard guard(h->device);
-  unsigned long long v[8];
+  unsigned long long v[16];
   HK_CUDA(cudaMemcpy(v, h->phaseClk, sizeof(v), cudaMemcpyDeviceToHost));
   for (int k = 0; k < 8; ++k) out_host8[k] = (double)v[k];
+  return HK_OK;
+}
+
+int hk_debug_finish_cycles(hk_env* h, double* out_host6) {
+  if (!h || !out_host6) return fail(HK_E_INVALID, "hk_debug_finish_cycles: NULL argument");
+  DeviceGuard guard(h->device);
+  unsigned long long v[16];
+  HK_CUDA(cudaMemcpy(v, h->phaseClk, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 6; ++k) out_host6[k] = (double)v[8 + k];
   return HK_OK;
 }
 

@@ -495,10 +495,119 @@ HK_HD_NOINLINE void commitCache(const Cache& cache, const Env& e) {
   }
 }
 
-// b2ContactManager::Collide
+HK_HD int ctz32(uint32_t m) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)m) - 1;
+#else
+  return __builtin_ctz(m);
+#endif
+}
+// The geometry half of b2Contact::Update for one non-sensor pair: manifold at the current poses, separation bound, and -- if
+// the shapes touch -- a manifold slot holding the new points with the warm-start impulses of the matching old ids.
+// No side effect on flags: collideApply() does the rest.  Returns the manifold point count.
+HK_HD_NOINLINE int collideEvaluate(const Scene& S, const Cache& cache, Env& e, int pid) {
+  Manifold tmp;
+  evaluateManifold(S, e, pid, &tmp);
+  setSep(e, pid, tmp.sepBound, tmp.sepNormal);
+  if (tmp.count > 0) {
+    const int oldCount = getCount(e, pid);
+    uint32_t oldKey[2] = {0, 0};
+    float oldNi[2] = {0, 0}, oldTi[2] = {0, 0};
+    for (int j = 0; j < oldCount; ++j) {
+      oldKey[j] = cache.at(pid, j);
+      oldNi[j] = u2f(cache.at(pid, 2 + 2 * j));
+      oldTi[j] = u2f(cache.at(pid, 3 + 2 * j));
+    }
+    for (int i = 0; i < tmp.count; ++i) {
+      tmp.ni[i] = 0.0f;
+      tmp.ti[i] = 0.0f;
+      for (int j = 0; j < oldCount; ++j) {
+        if (oldKey[j] == tmp.key[i]) {
+          tmp.ni[i] = oldNi[j];
+          tmp.ti[i] = oldTi[j];
+          break;
+        }
+      }
+    }
+    int slot;
+    if (e.nmf < MAX_MANIFOLDS) {
+      slot = e.nmf++;
+    } else {
+      slot = MAX_MANIFOLDS - 1;  // cannot happen in this scene; counted
+      e.nOverflow++;
+    }
+    e.mfPid[slot] = pid;
+    e.mf[slot] = tmp;
+  }
+  return tmp.count;
+}
+// The flag half of b2Contact::Update, in contact-list order: manifold point count, touching bit, wake-ups, BeginContact
+HK_HD void collideApply(const Scene& S, const Config& cfg, Env& e, int pid, bool touching, int count, bool sensor) {
+  const uint32_t bit = 1u << pid;
+  e.enabled |= bit;
+  const bool wasTouching = (e.touch & bit) != 0;
+  if (!sensor) {
+    setCount(e, pid, count);
+    if (touching != wasTouching) {
+      int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
+      if (bA >= 0) setAwake(e.b[bA], true);
+      if (bB >= 0) setAwake(e.b[bB], true);
+    }
+  }
+  if (touching) e.touch |= bit; else e.touch &= ~bit;
+  if (!wasTouching && touching) beginContact(cfg, e, pid);
+}
+
+// b2ContactManager::Collide.  b2Contact::Update is split: the geometry of every pair that will be updated is evaluated
+// first, ONE KIND OF PAIR AT A TIME (racket x static polygon, puck x static polygon, puck x racket, racket x racket, goal
+// sensors), so that the lanes of a warp -- whose contact lists hold different kinds in different positions -- run each
+// narrow-phase routine together instead of serialising all of them in every step of the list walk; the flags and events
+// are then applied in contact-list order, as Box2D does.  The poses do not change during Collide and bodies only ever wake
+// up in it, so the geometry does not depend on the order; a pair whose bodies were both asleep when the evaluation ran and
+// that a wake-up reaches later is evaluated on the spot (updateContact).  Only at the start of a world step (no manifold
+// slot is in use yet): the re-updates inside SolveTOI go through updateContact.
 HK_HD_NOINLINE void collide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
-  int i = 0;
   const uint32_t ov = e.ncontacts > 0 ? pairOverlapBits(S, e) : 0u;  // proxies do not move during Collide
+  // pairs that the list walk below will certainly update: they exist, their fat AABBs overlap, a body of theirs is awake
+  uint32_t todo = 0;
+  {
+    const uint32_t awakeMask = (e.b[0].awake ? HK_PAIRS_R1 : 0u) | (e.b[1].awake ? HK_PAIRS_R2 : 0u) | (e.b[2].awake ? HK_PAIRS_PUCK : 0u);
+    todo = e.exist & ov & awakeMask;
+  }
+  uint64_t counts = 0;      // 2 bits per pair: manifold point count of the evaluated pairs
+  uint32_t sensorTouch = 0;
+  for (uint32_t m = todo & 0x0000FFFFu; m;) {  // racket x static polygon
+    const int pid = ctz32(m);
+    m &= m - 1u;
+    counts |= (uint64_t)collideEvaluate(S, cache, e, pid) << (2 * pid);
+  }
+  for (uint32_t m = todo & 0x007E0000u; m;) {  // puck x static polygon
+    const int pid = ctz32(m);
+    m &= m - 1u;
+    counts |= (uint64_t)collideEvaluate(S, cache, e, pid) << (2 * pid);
+  }
+  for (uint32_t m = todo & 0x06000000u; m;) {  // puck x racket
+    const int pid = ctz32(m);
+    m &= m - 1u;
+    counts |= (uint64_t)collideEvaluate(S, cache, e, pid) << (2 * pid);
+  }
+  if (todo & 0x00010000u) counts |= (uint64_t)collideEvaluate(S, cache, e, 16) << 32;  // racket x racket
+  for (uint32_t m = todo & HK_PAIRS_SENSOR; m;) {  // puck x goal sensor
+    const int pid = ctz32(m);
+    m &= m - 1u;
+    const int fA = S.pairFA[pid];
+    // the GJK overlap test only when the puck centre is within reach of the goal box (margin >> float rounding)
+    AABB core = staticCoreAABB(S, fA);
+    V2 c = e.b[B_PUCK].p;
+    AABB pb;
+    pb.lx = pb.hx = c.x;
+    pb.ly = pb.hy = c.y;
+    bool touching;
+    if (aabbGap(core, pb) > S.puckRadius + HK_POLYGON_RADIUS + 0.005f) touching = false;
+    else touching = testOverlapPolyPuck(S.poly[fA], staticXf(S, fA), e.b[B_PUCK].p, S.puckRadius);
+    if (touching) sensorTouch |= 1u << pid;
+  }
+  int i = 0;
   while (i < e.ncontacts) {
     int pid = clistGet(e.clist, i);
     int bA = fixtureBody(S.pairFA[pid]), bB = fixtureBody(S.pairFB[pid]);
@@ -515,7 +624,13 @@ HK_HD_NOINLINE void collide(const Scene& S, const Config& cfg, const Cache& cach
       setCount(e, pid, 0);
       continue;
     }
-    updateContact(S, cfg, cache, e, pid);
+    if ((todo >> pid) & 1u) {
+      const bool sensor = ((HK_PAIRS_SENSOR >> pid) & 1u) != 0;
+      const int count = (int)((counts >> (2 * pid)) & 3u);
+      collideApply(S, cfg, e, pid, sensor ? ((sensorTouch >> pid) & 1u) != 0 : count > 0, count, sensor);
+    } else {
+      updateContact(S, cfg, cache, e, pid);  // woken during this walk
+    }
     ++i;
   }
 }

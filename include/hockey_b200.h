@@ -184,6 +184,9 @@ int hk_copy_stats(hk_env* env, double* dst_dev, void* stream);
 /* Diagnostics: block-cycles the general tiers spent in each tick phase since creation (synchronises the device).
  * out_host8 = tier 1 {policy+Collide, island solve, TOI, finish}, tier 2 {same}. */
 int hk_debug_phase_cycles(hk_env* env, double* out_host8);
+/* Diagnostics: block-cycles of the general tier's finish phase as warp 0 of each block saw them: {wait after the TOI
+ * barrier, cache commit, tickFinish (info / reward / outputs / auto-reset), state store, statistics flush, final barrier}. */
+int hk_debug_finish_cycles(hk_env* env, double* out_host6);
 /* Diagnostics (env created with HK_LANE_TRACE=1 in the environment): the last tick's general-tier trace,
  * [n/32+8 warps][4] cycles per tick phase of each warp, then [n][2] per-env work record (hk_lib.cu). */
 int hk_debug_lane_trace(hk_env* env, uint32_t* out_host, int64_t n_words);

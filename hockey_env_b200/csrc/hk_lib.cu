@@ -318,6 +318,16 @@ __host__ __device__ constexpr size_t rawBytes(int envLanes) {  // dynamic shared
 struct GenStamps {  // diagnostics: clock stamps of the phase boundaries of one general tick
   long long tc0, tc1, tc2, tc3, stampB, stampV, stampT, tf0, tfCommit, tfFinish, tfStore, tfFlush;
 };
+// Clock stamp AFTER a block barrier has completed.  BAR.SYNC.DEFER_BLOCKING does not hold the warp at the barrier
+// instruction: the next CS2R issues at once and the warp only blocks at its next memory instruction (measured on B200,
+// scripts/probes/bar_clock_probe.cu: a clock read right after __syncthreads() is 2 cycles after the one before it while
+// the other warp is still 100k cycles away).  So the stamp is taken behind a shared-memory load whose value it needs.
+__device__ __forceinline__ long long clockAfterBarrier(const Scene& S) {
+  const unsigned v = *reinterpret_cast<const volatile unsigned*>(&S.puckRadius);
+  long long t = 0;
+  if (v != 0xFFFFFFFFu) t = clock64();  // never equal (a float radius): the branch only ties the stamp to the load
+  return t;
+}
 // barrier among the threads that walk a general tick together: the whole block (k_general), or the general team of the
 // fused rollout kernel (its first `nthr` threads; the other warps of that block run fast ticks meanwhile)
 template <bool TEAM>
@@ -369,7 +379,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
   // phaseSync bit 0/1/2: block-wide barrier after Collide / after the island solve / after SolveTOI.  They keep the
   // warps of an SM in the same code region (shared instruction fetch); they are not needed for correctness.
   if (phaseSync & 1) teamSync<TEAM>(nthr);
-  long long& tc1 = gs.tc1; tc1 = clock64();
+  long long& tc1 = gs.tc1; tc1 = clockAfterBarrier(S);
   // ---- phase 2: island solve.  The velocity iterations of the whole block are pooled (see SolveTask): every lane files
   // its solve by loop shape, the warps of the block (helpers included) take one unit of one shape at a time.
   IslandCtx ctx;
@@ -390,7 +400,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
     if (threadIdx.x < 5) sRound[threadIdx.x] = 0;
     if (threadIdx.x == 0) *sSlowUnitP = 0;
     teamSync<TEAM>(nthr);
-    stampB = clock64();
+    stampB = clockAfterBarrier(S);
     const int nwarps = nthr >> 5;
     const int budget = (TIER == 1 && !unlimited) ? kMidSweeps : (1 << 20);
     const bool pool1 = (phaseSync & 8) != 0;  // also pool the single-contact solves
@@ -535,7 +545,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
       if (P.trace && __any_sync(0xffffffffu, inPlace) && lane == 0) atomicMax(sSlowUnitP, ((unsigned long long)(clock64() - tu0) << 8) | 11u);
     }
     teamSync<TEAM>(nthr);
-    stampV = clock64();
+    stampV = clockAfterBarrier(S);
     if (kind == HK_MULTI_KINDS + 1) {
       const Solve1Task& t = s1tasks[slot];
       ctx.vcs[0].pt[0].ni = t.vc.ni;
@@ -574,7 +584,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
   }
   const long long tw2 = clock64();
   if (phaseSync & 2) teamSync<TEAM>(nthr);
-  long long& tc2 = gs.tc2; tc2 = clock64();
+  long long& tc2 = gs.tc2; tc2 = clockAfterBarrier(S);
   // phase 3a-3c: first-pass TOI evaluations of the whole block as one task list, one task per thread
   const bool wantToi = valid && !e.aborted && (e.exist & HK_PAIRS_TOI);
   {
@@ -599,7 +609,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
     const int nwarps = nthr >> 5;
     for (int t = lane * nwarps + (threadIdx.x >> 5); t < total; t += nthr) sAlpha[t] = toiTaskRun(S, sTasks[t]);
     teamSync<TEAM>(nthr);
-    stampT = clock64();
+    stampT = clockAfterBarrier(S);
     for (int k = 0; k < nMine; ++k) {
       e.toiPre[mine[k].pid] = sAlpha[base + k];
       e.toiPreFlag |= 1u << mine[k].pid;
@@ -616,7 +626,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
     w[3] = (uint32_t)(tw3 - tw3a);
   }
   if (phaseSync & 4) teamSync<TEAM>(nthr);
-  long long& tc3 = gs.tc3; tc3 = clock64();
+  long long& tc3 = gs.tc3; tc3 = clockAfterBarrier(S);
   if (P.trace && (phaseSync & 4)) {  // diagnostics (HK_LANE_TRACE=1): block-wide max of per-lane TOI evaluation / event cycles
     __shared__ unsigned long long sMaxEval, sMaxEvent;
     if (threadIdx.x == 0) { sMaxEval = 0; sMaxEvent = 0; }
@@ -646,7 +656,7 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
       while (*((volatile const uint32_t*)io.waitFlag) != io.waitValue) __nanosleep(200);
     teamSync<TEAM>(nthr);
   }
-  const long long tf0 = clock64();
+  const long long tf0 = clockAfterBarrier(S);
   long long tf1 = tf0, tf2 = tf0;
   gs.tf0 = tf0;
   if (valid) {  // phase 4: commit, rewards, outputs, auto-reset, store
@@ -793,7 +803,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   __syncthreads();
   if (threadIdx.x == 0) {
     if (__any_sync(1u, valid) || true) {
-      long long tc4 = clock64();
+      long long tc4 = clockAfterBarrier(S);
       if (P.trace && TIER == 1 && blockIdx.x < P.n / 32 + 8) {
         uint32_t* w = P.trace + 4 * ((size_t)P.n / 32 + 8) + 2 * (size_t)P.n + 16 * (size_t)blockIdx.x;
         w[0] = (uint32_t)(tc1 - tc0);       // policy + Collide

@@ -12,7 +12,11 @@
 
 #if defined(__CUDACC__)
 #define HK_HD __host__ __device__ __forceinline__
+#if defined(HK_INLINE_ALL)  // experiment switch (scripts/ab_libs.sh): every helper inlined into its kernel
+#define HK_HD_NOINLINE __host__ __device__ __forceinline__
+#else
 #define HK_HD_NOINLINE __host__ __device__ __noinline__
+#endif
 #else
 #define HK_HD inline
 #define HK_HD_NOINLINE inline

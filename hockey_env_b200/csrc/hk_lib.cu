@@ -17,7 +17,9 @@
 
 #include "../../include/hockey_b200.h"
 #include "hk_tick.cuh"
+#if !defined(HK_TU_INLINE)
 #include "hk_actor.cuh"
+#endif
 
 using namespace hk;
 
@@ -111,6 +113,8 @@ __device__ __forceinline__ void flushStats(double* gstats, const TickStats& st) 
   }
 }
 
+}  // namespace
+namespace hkk {  // named: the struct is an argument of the launchers that cross the two passes of this file (hkinl, below)
 struct KParams {
   float4* core;
   uint32_t* cache;
@@ -124,9 +128,29 @@ struct KParams {
   int64_t env_id_offset;
   Config cfg;
 };
+}  // namespace hkk
+using hkk::KParams;
+// This file is compiled TWICE (hockey_env_b200/build.py) and the two objects are linked into one library:
+//   pass 1 (default)                         -- everything except the two kernels below; device helpers marked
+//                                               HK_HD_NOINLINE stay functions (k_fast is 2.4x slower fully inlined);
+//   pass 2 (-DHK_TU_INLINE -DHK_INLINE_ALL)  -- only k_general<1> and k_touch, with every helper inlined into the kernel
+//                                               (measured: general tier 0.462 -> 0.402 ms/tick at 65,536 envs, 2.61 ->
+//                                               2.32 at 1,048,576; touch tier 1.01 -> 0.95; profiles/README.md r2n).
+// Pass 1 reaches the kernels of pass 2 through these host functions; each pass has its own copy of the constant Scene.
+namespace hkinl {
+cudaError_t setScene(const hk::Scene& S);
+cudaError_t setMaxDynamicSmem(int bytes);
+size_t staticSmemGeneral();
+void setCarveouts(int pctGeneral, int pctTouch);
+void launchGeneral1(unsigned grid, int block, size_t smem, cudaStream_t stream, const KParams& P, const hk::StepIO& io, int unlimited,
+                    int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps);
+void launchTouch(unsigned grid, int block, cudaStream_t stream, const KParams& P, const hk::StepIO& io);
+}  // namespace hkinl
+namespace {
 
 constexpr int kSlowBlock = 384;  // one block per SM at 168 registers: all its warps walk the tick phases together
 
+#if !defined(HK_TU_INLINE)
 __global__ void __launch_bounds__(kBlock) k_create(KParams P) {
   __shared__ Scene S;
   stageScene(&S);
@@ -172,6 +196,7 @@ __global__ void __launch_bounds__(kBlock) k_step(KParams P, StepIO io) {
   flushStats(statsRow(P.stats), st);
 }
 
+#endif  // !HK_TU_INLINE
 // ---- the per-tick pipeline: k_fast over all envs, then the general path over the queues (three-tier cascade) ----------------
 // k_fast (tier 0) proves "nothing to solve" per env (hk_fast.cuh) and finishes those ticks with a small register
 // footprint; every other env index is appended to the tier-1 queue (one atomic per warp).  The general path
@@ -183,6 +208,7 @@ enum { Q_CLASSES = 4, QC_DONE1 = 4, QC_COUNT2 = 5, QC_DONE2 = 6 };
 
 // MINB = resident blocks per SM the register allocation aims at: 4 (120 registers, no spills) when the batch is one
 // wave anyway, 5 (96 registers) when occupancy pays (measured: profiles/README.md r1e)
+#if !defined(HK_TU_INLINE)
 template <int MINB>
 __global__ void __launch_bounds__(kBlock, MINB) k_fast(KParams P, StepIO io) {
   __shared__ Scene S;
@@ -233,6 +259,8 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast(KParams P, StepIO io) {
   flushStats(statsRow(P.stats), st);
 }
 
+#endif  // !HK_TU_INLINE
+#if defined(HK_TU_INLINE)  // pass 2 only (see hkinl above)
 // Touch tier: work class 0 of k_fast's queue (puck x racket contact ticks, i.e. every keep/shoot tick).  One contact,
 // one manifold point, no continuous-collision event possible -- the lanes of a warp all walk the same short path
 // (hk_fast.cuh worldStepTouch).  Envs whose proofs fail are appended to work class 3 for the general tier.
@@ -277,6 +305,7 @@ __global__ void __launch_bounds__(kBlock) k_touch(KParams P, StepIO io) {
   flushStats(statsRow(P.stats), st);
 }
 
+#endif  // HK_TU_INLINE
 // Tier 1 and 2 of the cascade run the same general path (hk::envTick) over compacted queues:
 //   TIER == 1 (k_mid): budgeted -- a velocity solve must converge (fixed point / short cycle) within kMidSweeps
 //                      sweeps and no continuous-collision EVENT may occur; otherwise the env is appended to the
@@ -856,6 +885,28 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
   }
 }
 
+#if defined(HK_TU_INLINE)
+}  // namespace
+namespace hkinl {
+cudaError_t setScene(const hk::Scene& S) { return cudaMemcpyToSymbol(c_scene, &S, sizeof(Scene)); }
+cudaError_t setMaxDynamicSmem(int bytes) { return cudaFuncSetAttribute(k_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
+size_t staticSmemGeneral() {
+  cudaFuncAttributes fa;
+  return cudaFuncGetAttributes(&fa, k_general<1>) == cudaSuccess ? fa.sharedSizeBytes : sizeof(Scene) + 2048;
+}
+void setCarveouts(int pctGeneral, int pctTouch) {
+  cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pctGeneral);
+  cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pctTouch);
+}
+void launchGeneral1(unsigned grid, int block, size_t smem, cudaStream_t stream, const KParams& P, const hk::StepIO& io, int unlimited,
+                    int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps) {
+  k_general<1><<<grid, block, smem, stream>>>(P, io, unlimited, lanesLog2, firstClass, phaseSync, envWarps, classWarps);
+}
+void launchTouch(unsigned grid, int block, cudaStream_t stream, const KParams& P, const hk::StepIO& io) {
+  k_touch<<<grid, block, 0, stream>>>(P, io);
+}
+}  // namespace hkinl
+#else  // pass 1: the rest of the file
 // K fused ticks: body state stays in registers/local memory across ticks, HBM state traffic is paid once
 __global__ void __launch_bounds__(kBlock) k_rollout(KParams P, StepIO io, int k_steps) {
   __shared__ Scene S;
@@ -1251,10 +1302,9 @@ struct hk_env {
     const size_t stat = staticSmem;
     const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
     const int perSmAuto = std::max(1, (targetBlocks + sms - 1) / sms);  // automatic shape: blocks per SM the target asks for
-    cudaFuncSetAttribute(k_general<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)));
+    hkinl::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat * 3));
     cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
     cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
-    cudaFuncSetAttribute(k_touch, cudaFuncAttributePreferredSharedMemoryCarveout, pct(stat * 3));
     cudaFuncSetAttribute(k_rollout_fused, cudaFuncAttributePreferredSharedMemoryCarveout, pct(rawBytes(kSlowBlock) + stat + sizeof(FusedShared)));
   }
   // Per-kernel timing (hk_kernel_timing): CUDA events recorded on the launching stream around every kernel of a tick,
@@ -1282,13 +1332,13 @@ struct hk_env {
     if (n < 100000) k_fast<4><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     else k_fast<5><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     stamp(1, stream);
-    if (touch) k_touch<<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    if (touch) hkinl::launchTouch((unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, stream, params(), io);
     stamp(2, stream);
     if (between) between(this, stream, betweenArg);
     const StepIO& iog = ioGeneral ? *ioGeneral : io;
     const int b2 = blockTier2(), w2 = b2 / 32;
-    k_general<1><<<gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream>>>(
-        params(), iog, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
+    hkinl::launchGeneral1(gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream, params(), iog,
+                          tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
     stamp(3, stream);
     if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), iog, 1, lanes2, 0, phaseSync, w2, 0);
     stamp(4, stream);
@@ -1378,7 +1428,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 16) sms = 148;
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, k_general<1>) == cudaSuccess) h->staticSmem = fa.sharedSizeBytes;
+    h->staticSmem = hkinl::staticSmemGeneral();
     if (cudaFuncGetAttributes(&fa, k_fast<4>) == cudaSuccess) h->fastSmem = fa.sharedSizeBytes;
     h->sms = sms;
     if (const char* f = getenv("HK_FUSED")) h->fused = f[0] != '0';
@@ -1391,7 +1441,8 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   std::memset(&S, 0, sizeof(S));
   scene_build::build(&S);
   cudaError_t err = cudaMemcpyToSymbol(c_scene, &S, sizeof(Scene));
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
+  if (err == cudaSuccess) err = hkinl::setScene(S);
+  if (err == cudaSuccess) err = hkinl::setMaxDynamicSmem((int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_general<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_rollout_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);
@@ -1835,3 +1886,4 @@ int hk_stats_device_ptr(hk_env* h, double** out_dev) {
 }
 
 }  // extern "C"
+#endif  // !HK_TU_INLINE (pass 1)

@@ -23,7 +23,11 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
 ]
 LINK_FLAGS = ["-shared", "--cudart", "shared"]  # libcudart.so of the process (torch ships one): no second copy of the runtime
-PASS2_FLAGS = ["-DHK_TU_INLINE", "-DHK_INLINE_ALL"]
+# inlining groups (hk_math.cuh), measured on the B200 (profiles/README.md, "inlining"): pass 1 keeps the helpers as
+# functions except force shaping / info / tick epilogue, the sin-cos polynomial and the swept-AABB update (k_fast -15 %;
+# inlining its contact-list walk makes it 2.2x SLOWER); pass 2 inlines everything except the contact-list walk of Collide
+PASS1_FLAGS = ["-DHK_IN_FASTA", "-DHK_IN_MATH", "-DHK_IN_FASTW2"]
+PASS2_FLAGS = ["-DHK_TU_INLINE", "-DHK_INLINE_ALL", "-DHK_OUT_COLLIDE"]
 
 
 def sources():
@@ -49,7 +53,7 @@ def build_cuda(force=False, verbose=False, so=SO, pass2_flags=None, tag=""):
     v = ["-Xptxas", "-v"] if verbose else []
     o1, o2 = os.path.join(OBJ_DIR, f"hk_lib{tag}.o"), os.path.join(OBJ_DIR, f"hk_inl{tag}.o")
     p2 = PASS2_FLAGS if pass2_flags is None else list(pass2_flags)
-    procs = [subprocess.Popen([nvcc] + NVCC_FLAGS + v + ["-c", "-o", o1, src]),
+    procs = [subprocess.Popen([nvcc] + NVCC_FLAGS + v + PASS1_FLAGS + ["-c", "-o", o1, src]),
              subprocess.Popen([nvcc] + NVCC_FLAGS + v + p2 + ["-c", "-o", o2, src])]
     rcs = [p.wait() for p in procs]
     if any(rcs):

@@ -31,7 +31,7 @@ HK_HD V2 polyV(const Poly& p, int i) { return mk(p.vx[i], p.vy[i]); }
 HK_HD V2 polyN(const Poly& p, int i) { return mk(p.nx[i], p.ny[i]); }
 
 // ---- polygon (A) vs circle (B, centre at body origin) -------------------------------------------
-HK_HD_NOINLINE void collidePolygonCircle(Manifold* m, const Poly& polyA, const Xf& xfA, V2 circleCenterWorld, float circleRadius) {
+HK_NI_NARROW void collidePolygonCircle(Manifold* m, const Poly& polyA, const Xf& xfA, V2 circleCenterWorld, float circleRadius) {
   m->count = 0;
   m->sepBound = -HK_MAXFLOAT;
   m->sepNormal = mk(0.0f, 0.0f);
@@ -178,7 +178,7 @@ HK_HD int clipSegmentToLine(ClipVertex vOut[2], const ClipVertex vIn[2], V2 norm
   return numOut;
 }
 
-HK_HD_NOINLINE void collidePolygons(Manifold* m, const Poly& polyA, const Xf& xfA, const Poly& polyB, const Xf& xfB) {
+HK_NI_NARROW void collidePolygons(Manifold* m, const Poly& polyA, const Xf& xfA, const Poly& polyB, const Xf& xfB) {
   m->count = 0;
   const float totalRadius = HK_POLYGON_RADIUS + HK_POLYGON_RADIUS;
   int edgeA = 0;
@@ -396,7 +396,7 @@ HK_HD void simplexSolve3(Simplex& s) {
 }
 
 // returns the core distance (useRadii handled by the caller); fills witness points
-HK_HD_NOINLINE float gjkDistance(SimplexCache* cache, const Proxy& proxyA, const Xf& xfA, const Proxy& proxyB,
+HK_NI_TOI float gjkDistance(SimplexCache* cache, const Proxy& proxyA, const Xf& xfA, const Proxy& proxyB,
                                  const Xf& xfB, V2* pointA, V2* pointB) {
   Simplex simplex;
   // ReadCache
@@ -481,7 +481,7 @@ HK_HD_NOINLINE float gjkDistance(SimplexCache* cache, const Proxy& proxyA, const
 }
 
 // b2TestOverlap(shapeA, shapeB, xfA, xfB): sensor test of b2Contact::Update (goal polygon vs puck)
-HK_HD_NOINLINE bool testOverlapPolyPuck(const Poly& poly, const Xf& xfA, V2 puckCenter, float puckRadius) {
+HK_NI_TOI bool testOverlapPolyPuck(const Poly& poly, const Xf& xfA, V2 puckCenter, float puckRadius) {
   Proxy pa, pb;
   pa.poly = &poly;
   pa.radius = HK_POLYGON_RADIUS;
@@ -510,7 +510,7 @@ struct SepFn {
   V2 localPoint, axis;
 };
 
-HK_HD_NOINLINE float sepFindMin(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int* indexA,
+HK_NI_TOI float sepFindMin(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int* indexA,
                        int* indexB, float t) {
   Xf xfA, xfB;
   sweepXf(sA, &xfA, t);
@@ -542,7 +542,7 @@ HK_HD_NOINLINE float sepFindMin(const SepFn& f, const Proxy& pA, const Sweep& sA
   }
 }
 
-HK_HD_NOINLINE float sepEvaluate(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int indexA,
+HK_NI_TOI float sepEvaluate(const SepFn& f, const Proxy& pA, const Sweep& sA, const Proxy& pB, const Sweep& sB, int indexA,
                         int indexB, float t) {
   Xf xfA, xfB;
   sweepXf(sA, &xfA, t);
@@ -564,7 +564,7 @@ HK_HD_NOINLINE float sepEvaluate(const SepFn& f, const Proxy& pA, const Sweep& s
   }
 }
 
-HK_HD_NOINLINE void timeOfImpact(int* outState, float* outT, const Proxy& proxyA, const Sweep& sweepAin,
+HK_NI_TOI void timeOfImpact(int* outState, float* outT, const Proxy& proxyA, const Sweep& sweepAin,
                                  const Proxy& proxyB, const Sweep& sweepBin, float tMax) {
   *outState = TOI_UNKNOWN;
   *outT = tMax;

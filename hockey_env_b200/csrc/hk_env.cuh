@@ -38,7 +38,7 @@ HK_HD void checkBoundaries(double force[2], Body& player, bool is_one) {
 }
 
 // _apply_translation_action_with_max_speed (hockey_env.py:436-470), max_speed = 10
-HK_HD_NOINLINE void applyTranslation(const Scene& S, Body& player, int bi, float a0, float a1, bool is_one) {
+HK_NI_FASTA void applyTranslation(const Scene& S, Body& player, int bi, float a0, float a1, bool is_one) {
   const double timeStep = 1.0 / HK_FPS;
   const double max_speed = 10;
   double vel0 = (double)player.v.x, vel1 = (double)player.v.y;
@@ -86,7 +86,7 @@ HK_HD_NOINLINE void applyTranslation(const Scene& S, Body& player, int bi, float
 }
 
 // _apply_rotation_action_with_max_speed (hockey_env.py:472-483)
-HK_HD_NOINLINE void applyRotation(const Scene& S, Body& player, int bi, float action) {
+HK_NI_FASTA void applyRotation(const Scene& S, Body& player, int bi, float action) {
   const double timeStep = 1.0 / HK_FPS;
   double angle = player.a;
   double torque = (double)(action * (float)HK_TORQUEMULTIPLIER);
@@ -106,7 +106,7 @@ HK_HD void keepPuck(const Scene& S, Env& e, const Body& player) {
   setTransformPuck(S, e, player.p);
   setLinearVelocity(e.b[B_PUCK], player.v);
 }
-HK_HD_NOINLINE void shoot(const Scene& S, Env& e, const Body& player, bool is_one) {
+HK_NI_RARE void shoot(const Scene& S, Env& e, const Body& player, bool is_one) {
   Body& puck = e.b[B_PUCK];
   double s, c;
   sincos_poly((double)player.a, &s, &c);
@@ -138,7 +138,7 @@ HK_HD void getObs2(const Env& e, float* o) {
 }
 
 // _get_info / get_info_agent_two (hockey_env.py:542-591): out = winner, closeness, touch, direction
-HK_HD_NOINLINE void getInfo(const Config& cfg, const Env& e, bool agent_two, double* out) {
+HK_NI_FASTA void getInfo(const Config& cfg, const Env& e, bool agent_two, double* out) {
   const Body &p1 = e.b[B_R1], &p2 = e.b[B_R2], &pk = e.b[B_PUCK];
   double closeness = 0;
   bool cond = agent_two ? ((double)pk.p.x > HK_CENTER_X && (double)pk.v.x >= 0) : ((double)pk.p.x < HK_CENTER_X && (double)pk.v.x <= 0);
@@ -168,7 +168,7 @@ HK_HD double computeReward(const Env& e) {  // hockey_env.py:518-528
 }
 
 // BasicOpponent.act (hockey_env.py:787-833) on a float32 observation
-HK_HD_NOINLINE void basicAct(const Config& cfg, const float* obs, bool weak, double* phase_io, double u_inc, float out[4]) {
+HK_NI_POLICY void basicAct(const Config& cfg, const float* obs, bool weak, double* phase_io, double u_inc, float out[4]) {
   double p1[3] = {obs[0], obs[1], obs[2]};
   double v1[3] = {obs[3], obs[4], obs[5]};
   double puck0 = obs[12], puck1 = obs[13], puckv0 = obs[14], puckv1 = obs[15];
@@ -241,7 +241,7 @@ HK_HD void createDynamicBody(const Scene& S, Env& e, int bi, double px, double p
   e.fat[bi].hx = a.hx + HK_AABB_EXTENSION;
   e.fat[bi].hy = a.hy + HK_AABB_EXTENSION;
 }
-HK_HD_NOINLINE void envReset(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, int one_starting /* -1 = alternate */,
+HK_NI_RARE void envReset(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, int one_starting /* -1 = alternate */,
                              int64_t reset_seed = -1) {
   e.done = false;
   e.winner = 0;
@@ -292,7 +292,7 @@ HK_HD_NOINLINE void envReset(const Scene& S, const Config& cfg, Env& e, uint64_t
 }
 
 // actions for this tick from the per-player policy (include/hockey_b200.h HK_POLICY_*)
-HK_HD_NOINLINE void policyActions(const Config& cfg, Env& e, uint64_t env_id, const float* ext /* this env's row or null */,
+HK_NI_POLICY void policyActions(const Config& cfg, Env& e, uint64_t env_id, const float* ext /* this env's row or null */,
                          int pol1, int pol2, float a[8]) {
   const int pol[2] = {pol1, pol2};
   U4 ro;

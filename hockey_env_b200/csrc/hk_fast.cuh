@@ -42,7 +42,7 @@ HK_HD int bailClass(int kind) {
 // updated exactly (b2Contact::Update with manifold, warm-start ids, BeginContact) and may touch; every other pair
 // must still be provably clear.
 template <bool PUCK_RACKET>
-HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
+HK_NI_FASTW1 bool collideFast(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   int i = 0;
   const uint32_t ov = e.ncontacts > 0 ? pairOverlapBits(S, e) : 0u;  // proxies do not move during Collide
   while (i < e.ncontacts) {
@@ -125,7 +125,7 @@ HK_HD_NOINLINE bool collideFast(const Scene& S, const Config& cfg, const Cache& 
 }
 
 // synchronizeFixtures that also keeps the tight swept box; q0 = rotation at the sweep start (== b.q before the move)
-HK_HD_NOINLINE void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot q0, AABB* keep) {
+HK_NI_FASTW2 void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot q0, AABB* keep) {
   Body& b = e.b[bi];
   Xf xf1;
   xf1.q = q0;
@@ -141,7 +141,7 @@ HK_HD_NOINLINE void synchronizeFixturesKeep(const Scene& S, Env& e, int bi, Rot 
   moveProxy(e, bi, comb, b.p - xf1.p);
 }
 
-HK_HD_NOINLINE bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float h) {
+HK_NI_FASTW bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float h) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   e.sepValid = 0;

@@ -12,14 +12,93 @@
 
 #if defined(__CUDACC__)
 #define HK_HD __host__ __device__ __forceinline__
-#if defined(HK_INLINE_ALL)  // experiment switch (scripts/ab_libs.sh): every helper inlined into its kernel
-#define HK_HD_NOINLINE __host__ __device__ __forceinline__
+// The large device helpers are functions in pass 1 of hk_lib.cu and inlined in pass 2 (-DHK_INLINE_ALL; see hk_lib.cu,
+// namespace hkinl).  They are tagged by group so that a build can keep one group out of line in pass 2 (-DHK_OUT_<G>) or
+// inline it in pass 1 (-DHK_IN_<G>): the A/B switches behind profiles/README.md's inlining table.
+#define HK_FN_INLINE __host__ __device__ __forceinline__
+#define HK_FN_OUTLINE inline __host__ __device__ __noinline__  // `inline`: one (weak) host definition although both passes of hk_lib.cu hold it
+#if defined(HK_INLINE_ALL)
+#define HK_HD_NOINLINE HK_FN_INLINE
 #else
-#define HK_HD_NOINLINE __host__ __device__ __noinline__
+#define HK_HD_NOINLINE HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_RARE)) || defined(HK_IN_RARE)
+#define HK_NI_RARE HK_FN_INLINE      // reset, controllers, shoot: run by few lanes per tick
+#else
+#define HK_NI_RARE HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_TOI)) || defined(HK_IN_TOI)
+#define HK_NI_TOI HK_FN_INLINE       // b2TimeOfImpact, GJK, separation function
+#else
+#define HK_NI_TOI HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_LOOP)) || defined(HK_IN_LOOP)
+#define HK_NI_LOOP HK_FN_INLINE      // register-resident velocity-iteration loops
+#else
+#define HK_NI_LOOP HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_NARROW)) || defined(HK_IN_NARROW)
+#define HK_NI_NARROW HK_FN_INLINE    // manifold routines and b2Contact::Update
+#else
+#define HK_NI_NARROW HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_MATH)) || defined(HK_IN_MATH)
+#define HK_NI_MATH HK_FN_INLINE      // sin/cos polynomial
+#else
+#define HK_NI_MATH HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_FASTW)) || defined(HK_IN_FASTW)
+#define HK_NI_FASTW HK_FN_INLINE     // the fast tier's world step
+#else
+#define HK_NI_FASTW HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_COLLIDE)) || defined(HK_IN_COLLIDE)
+#define HK_NI_COLLIDE HK_FN_INLINE   // b2ContactManager::Collide (the contact-list walk)
+#else
+#define HK_NI_COLLIDE HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_POLICY)) || defined(HK_IN_POLICY)
+#define HK_NI_POLICY HK_FN_INLINE    // in-kernel controllers
+#else
+#define HK_NI_POLICY HK_FN_OUTLINE
+#endif
+#if defined(HK_IN_FASTW1) && !defined(HK_OUT_FASTW1)
+#define HK_NI_FASTW1 HK_FN_INLINE
+#elif defined(HK_OUT_FASTW1)
+#define HK_NI_FASTW1 HK_FN_OUTLINE
+#else
+#define HK_NI_FASTW1 HK_NI_FASTW
+#endif
+#if defined(HK_IN_FASTW2)
+#define HK_NI_FASTW2 HK_FN_INLINE
+#else
+#define HK_NI_FASTW2 HK_NI_FASTW
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_FASTA)) || defined(HK_IN_FASTA)
+#define HK_NI_FASTA HK_FN_INLINE     // force shaping, info, tick epilogue
+#else
+#define HK_NI_FASTA HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_FASTS)) || defined(HK_IN_FASTS)
+#define HK_NI_FASTS HK_FN_INLINE     // proxy AABBs and the pair scan
+#else
+#define HK_NI_FASTS HK_FN_OUTLINE
 #endif
 #else
 #define HK_HD inline
 #define HK_HD_NOINLINE inline
+#define HK_NI_FASTW inline
+#define HK_NI_COLLIDE inline
+#define HK_NI_POLICY inline
+#define HK_NI_FASTW1 inline
+#define HK_NI_FASTW2 inline
+#define HK_NI_FASTA inline
+#define HK_NI_FASTS inline
+#define HK_NI_RARE inline
+#define HK_NI_TOI inline
+#define HK_NI_LOOP inline
+#define HK_NI_NARROW inline
+#define HK_NI_MATH inline
 #endif
 
 namespace hk {
@@ -96,7 +175,7 @@ HK_HD float fabs2(float a) { return a > 0.0f ? a : -a; }
 // sin/cos evaluated in double by a fixed polynomial (fdlibm kernel coefficients, Cody-Waite
 // reduction) and rounded to float: equals the correctly rounded sinf/cosf for all but ~1e-8 of
 // arguments and is bit-identical on host and device (no libm / libdevice dependence).
-HK_HD_NOINLINE void sincos_poly(double x, double* s, double* c) {
+HK_NI_MATH void sincos_poly(double x, double* s, double* c) {
   const double kd = rint(x * 0.63661977236758134308);
   const long long k = (long long)kd;
   double r = (x - kd * 1.57079632673412561417e+00) - kd * 6.07710050650619224932e-11;
@@ -199,7 +278,7 @@ HK_HD bool aabbOverlap(const AABB& a, const AABB& b) {
 struct U4 {
   uint32_t x, y, z, w;
 };
-HK_HD_NOINLINE U4 philox(uint64_t seed, uint64_t env, uint32_t c2, uint32_t c3) {
+HK_NI_RARE U4 philox(uint64_t seed, uint64_t env, uint32_t c2, uint32_t c3) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)env, c1 = (uint32_t)(env >> 32);
 #pragma unroll

@@ -84,7 +84,7 @@ __device__ __forceinline__ void warpStoreRows18(float* __restrict__ dst, const f
 // `write` = false suppresses all per-tick outputs (fused rollout, all but the last tick).
 // deferRows != null (k_fast): the caller writes the obs row (and the final_obs row unless this env was reset here)
 // warp-cooperatively after the call; *deferRows is set when this call already wrote the env's terminal final_obs row.
-HK_HD_NOINLINE void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io, bool write,
+HK_NI_FASTA void tickFinish(const Scene& S, const Config& cfg, Env& e, uint64_t env_id, size_t i, const StepIO& io, bool write,
                       TickStats& st, int had1, int had2, bool* deferRows = nullptr) {
   double inf[4], inf2[4];
   getInfo(cfg, e, false, inf);

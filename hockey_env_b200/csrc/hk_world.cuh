@@ -200,7 +200,7 @@ HK_HD AABB fixtureFat(const Scene& S, const Env& e, int f) { return f < N_STATIC
 HK_HD int staticBodyOf(int f) { return f < 6 ? f : (f < 8 ? 6 : 7); }
 
 // ---- fixture AABB / broad-phase proxy (b2Fixture::Synchronize, b2DynamicTree::MoveProxy) ----------
-HK_HD_NOINLINE AABB shapeAABB(const Scene& S, int bi, const Xf& xf) {
+HK_NI_FASTS AABB shapeAABB(const Scene& S, int bi, const Xf& xf) {
   AABB r;
   if (bi == B_PUCK) {
     float rad = S.puckRadius;
@@ -252,7 +252,7 @@ HK_HD_NOINLINE void synchronizeFixtures(const Scene& S, Env& e, int bi) {
   moveProxy(e, bi, comb, b.p - xf1.p);
 }
 // b2Body::SetTransform (puck teleport, hockey_env.py:619)
-HK_HD_NOINLINE void setTransformPuck(const Scene& S, Env& e, V2 position) {
+HK_NI_RARE void setTransformPuck(const Scene& S, Env& e, V2 position) {
   Body& b = e.b[B_PUCK];
   b.q = rotIdentity();
   b.p = position;
@@ -286,7 +286,7 @@ HK_HD uint32_t pairOverlapBits(const Scene& S, const Env& e) {
 }
 
 // b2ContactManager::FindNewContacts for the buffered proxy moves
-HK_HD_NOINLINE void findNewContacts(const Scene& S, Env& e) {
+HK_NI_FASTS void findNewContacts(const Scene& S, Env& e) {
   uint32_t mv = e.moved & 7u;
   e.moved &= ~7u;
   if (!mv) return;
@@ -379,7 +379,7 @@ HK_HD float polyStaticFaceGap(const Scene& S, int f, const Poly& PB, const Xf& x
   return best;
 }
 
-HK_HD_NOINLINE void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
+HK_NI_NARROW void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
   int fA = S.pairFA[pid], fB = S.pairFB[pid];
   Xf xfA = fixtureXf(S, e, fA);
   if (fB == F_PUCK) {
@@ -405,7 +405,7 @@ HK_HD_NOINLINE void evaluateManifold(const Scene& S, const Env& e, int pid, Mani
 // b2Contact::Update.  Manifold ids and warm-start impulses of the contacts handled this tick live in the
 // manifold slots; the global cache is read the first time a pair is updated in a tick and written once, by
 // commitCache(), when the tick completes.
-HK_HD_NOINLINE void updateContact(const Scene& S, const Config& cfg, const Cache& cache, Env& e, int pid) {
+HK_NI_NARROW void updateContact(const Scene& S, const Config& cfg, const Cache& cache, Env& e, int pid) {
   const uint32_t bit = 1u << pid;
   e.enabled |= bit;
   const bool wasTouching = (e.touch & bit) != 0;
@@ -505,7 +505,7 @@ HK_HD int ctz32(uint32_t m) {
 // The geometry half of b2Contact::Update for one non-sensor pair: manifold at the current poses, separation bound, and -- if
 // the shapes touch -- a manifold slot holding the new points with the warm-start impulses of the matching old ids.
 // No side effect on flags: collideApply() does the rest.  Returns the manifold point count.
-HK_HD_NOINLINE int collideEvaluate(const Scene& S, const Cache& cache, Env& e, int pid) {
+HK_NI_NARROW int collideEvaluate(const Scene& S, const Cache& cache, Env& e, int pid) {
   Manifold tmp;
   evaluateManifold(S, e, pid, &tmp);
   setSep(e, pid, tmp.sepBound, tmp.sepNormal);
@@ -566,7 +566,7 @@ HK_HD void collideApply(const Scene& S, const Config& cfg, Env& e, int pid, bool
 // up in it, so the geometry does not depend on the order; a pair whose bodies were both asleep when the evaluation ran and
 // that a wake-up reaches later is evaluated on the spot (updateContact).  Only at the start of a world step (no manifold
 // slot is in use yet): the re-updates inside SolveTOI go through updateContact.
-HK_HD_NOINLINE void collide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
+HK_NI_COLLIDE void collide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   const uint32_t ov = e.ncontacts > 0 ? pairOverlapBits(S, e) : 0u;  // proxies do not move during Collide
   // pairs that the list walk below will certainly update: they exist, their fat AABBs overlap, a body of theirs is awake
   uint32_t todo = 0;
@@ -943,7 +943,7 @@ HK_HD VC1 vc1Of(const VC& vc) {
 // a fixed point stays a fixed point, and a period-2 cycle found later is resolved by the parity of the ABSOLUTE sweep
 // index, so the result does not depend on the cuts.
 enum { HK_SOLVE_UNFINISHED = -2 };
-HK_HD_NOINLINE int runVelocityIterations1Range(VC1& vc, Vel& A, Vel& B, int budget, int velIters, int itStart, int itStop,
+HK_NI_LOOP int runVelocityIterations1Range(VC1& vc, Vel& A, Vel& B, int budget, int velIters, int itStart, int itStop,
                                                int* sweepsOut) {
   int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
@@ -1038,7 +1038,7 @@ HK_HD int runVelocityIterations1(Env& e, VC& vc, int velIters) {
 
 // Same for one contact with a two-point manifold (racket resting on a wall / goal): tangent rows, then the 2x2
 // block solver of b2ContactSolver::SolveVelocityConstraints, all in registers.
-HK_HD_NOINLINE int runVelocityIterations2Core(VC& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
+HK_NI_LOOP int runVelocityIterations2Core(VC& vc, Vel& A, Vel& B, int budget, int velIters, int* sweepsOut) {
   int sweeps = 0;
   const float mA = vc.mA, iA = vc.iA, mB = vc.mB, iB = vc.iB;
   const V2 normal = vc.normal;
@@ -1395,7 +1395,7 @@ HK_HD void vcrStoreImpulses(const VCR& c, VC& m) {
 // `vcs` may live anywhere (the caller's local array, or a block-shared task record another lane filled in: hk_lib.cu
 // hands the multi-contact solves of a block to warps that each run ONE loop shape)
 template <int C0, int C1, int C2>  // C2 == 0: two contacts
-HK_HD_NOINLINE int runVelocityIterationsFixedCore(VC* vcs, VelTriple& vio, int budget, int velIters, int* sweepsOut) {
+HK_NI_LOOP int runVelocityIterationsFixedCore(VC* vcs, VelTriple& vio, int budget, int velIters, int* sweepsOut) {
   int sweeps = 0;
   VelTriple v = vio;  // registers for the whole loop
   VCR a, b, c;

@@ -2,8 +2,8 @@
 
 csrc/hk_lib.cu is compiled twice and the two objects are linked into one shared library (see the comment at
 `namespace hkinl` in hk_lib.cu): pass 1 is the whole library with the large device helpers kept as functions, pass 2
-(-DHK_TU_INLINE -DHK_INLINE_ALL) holds only the general-tier and touch-tier kernels with every helper inlined.  The two
-passes run in parallel.
+(-DHK_TU_INLINE -DHK_INLINE_ALL) holds only the general-tier and touch-tier kernels with every helper inlined, and is built
+twice (register budgets for blocks of up to 384 and up to 256 threads).  The three compilations run in parallel.
 """
 import os
 import shutil
@@ -28,6 +28,7 @@ LINK_FLAGS = ["-shared", "--cudart", "shared"]  # libcudart.so of the process (t
 # inlining its contact-list walk makes it 2.2x SLOWER); pass 2 inlines everything except the contact-list walk of Collide
 PASS1_FLAGS = ["-DHK_IN_FASTA", "-DHK_IN_MATH", "-DHK_IN_FASTW2"]
 PASS2_FLAGS = ["-DHK_TU_INLINE", "-DHK_INLINE_ALL", "-DHK_OUT_COLLIDE"]
+PASS2B_FLAGS = ["-DHK_INL_NS=hkinl256", "-DHK_GENERAL_BOUND=256"]  # on top of pass 2's: the same kernel for blocks of <= 256 threads
 
 
 def sources():
@@ -51,14 +52,15 @@ def build_cuda(force=False, verbose=False, so=SO, pass2_flags=None, tag=""):
     os.makedirs(OBJ_DIR, exist_ok=True)
     src = os.path.join(CSRC, "hk_lib.cu")
     v = ["-Xptxas", "-v"] if verbose else []
-    o1, o2 = os.path.join(OBJ_DIR, f"hk_lib{tag}.o"), os.path.join(OBJ_DIR, f"hk_inl{tag}.o")
+    o1, o2, o3 = (os.path.join(OBJ_DIR, f"{n}{tag}.o") for n in ("hk_lib", "hk_inl", "hk_inl256"))
     p2 = PASS2_FLAGS if pass2_flags is None else list(pass2_flags)
     procs = [subprocess.Popen([nvcc] + NVCC_FLAGS + v + PASS1_FLAGS + ["-c", "-o", o1, src]),
-             subprocess.Popen([nvcc] + NVCC_FLAGS + v + p2 + ["-c", "-o", o2, src])]
+             subprocess.Popen([nvcc] + NVCC_FLAGS + v + p2 + ["-c", "-o", o2, src]),
+             subprocess.Popen([nvcc] + NVCC_FLAGS + v + p2 + PASS2B_FLAGS + ["-c", "-o", o3, src])]
     rcs = [p.wait() for p in procs]
     if any(rcs):
-        raise RuntimeError(f"nvcc failed (pass 1 rc={rcs[0]}, pass 2 rc={rcs[1]})")
-    subprocess.check_call([nvcc] + LINK_FLAGS + ["-o", so, o1, o2])
+        raise RuntimeError(f"nvcc failed (pass 1 rc={rcs[0]}, pass 2 rc={rcs[1]}, pass 2b rc={rcs[2]})")
+    subprocess.check_call([nvcc] + LINK_FLAGS + ["-o", so, o1, o2, o3])
     return so
 
 

@@ -133,19 +133,25 @@ using hkk::KParams;
 // This file is compiled TWICE (hockey_env_b200/build.py) and the two objects are linked into one library:
 //   pass 1 (default)                         -- everything except the two kernels below; device helpers marked
 //                                               HK_HD_NOINLINE stay functions (k_fast is 2.4x slower fully inlined);
-//   pass 2 (-DHK_TU_INLINE -DHK_INLINE_ALL)  -- only k_general<1> and k_touch, with every helper inlined into the kernel
+//   pass 2 (-DHK_TU_INLINE -DHK_INLINE_ALL)  -- only k_general<1> and k_touch, with every helper inlined into the kernel;
+//                                               built twice (HK_INL_NS / HK_GENERAL_BOUND): blocks of up to 384 threads at 168
+//                                               registers, and blocks of up to 256 threads at up to 255 registers (-2.6 %)
 //                                               (measured: general tier 0.462 -> 0.402 ms/tick at 65,536 envs, 2.61 ->
 //                                               2.32 at 1,048,576; touch tier 1.01 -> 0.95; profiles/README.md r2n).
 // Pass 1 reaches the kernels of pass 2 through these host functions; each pass has its own copy of the constant Scene.
-namespace hkinl {
-cudaError_t setScene(const hk::Scene& S);
-cudaError_t setMaxDynamicSmem(int bytes);
-size_t staticSmemGeneral();
-void setCarveouts(int pctGeneral, int pctTouch);
-void launchGeneral1(unsigned grid, int block, size_t smem, cudaStream_t stream, const KParams& P, const hk::StepIO& io, int unlimited,
-                    int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps);
-void launchTouch(unsigned grid, int block, cudaStream_t stream, const KParams& P, const hk::StepIO& io);
-}  // namespace hkinl
+#define HK_INL_DECLS                                                                                                              \
+  cudaError_t setScene(const hk::Scene& S);                                                                                       \
+  cudaError_t setMaxDynamicSmem(int bytes);                                                                                       \
+  size_t staticSmemGeneral();                                                                                                     \
+  void setCarveouts(int pctGeneral, int pctTouch);                                                                                \
+  void launchGeneral1(unsigned grid, int block, size_t smem, cudaStream_t stream, const KParams& P, const hk::StepIO& io,         \
+                      int unlimited, int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps);                 \
+  void launchTouch(unsigned grid, int block, cudaStream_t stream, const KParams& P, const hk::StepIO& io);
+namespace hkinl { HK_INL_DECLS }     // pass 2:  k_general<1> bounded to 384 threads (168 registers), k_touch
+namespace hkinl256 { HK_INL_DECLS }  // pass 2b: k_general<1> bounded to 256 threads (up to 255 registers): the blocks of batches <= 100k envs
+#if !defined(HK_INL_NS)
+#define HK_INL_NS hkinl
+#endif
 namespace {
 
 constexpr int kSlowBlock = 384;  // one block per SM at 168 registers: all its warps walk the tick phases together
@@ -727,7 +733,10 @@ __device__ __forceinline__ void generalTick(const KParams& P, const StepIO& io, 
 }
 
 template <int TIER>
-__global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps) {
+#if !defined(HK_GENERAL_BOUND)
+#define HK_GENERAL_BOUND kSlowBlock  // A/B switch: 256 lets ptxas use up to 255 registers (only valid for blocks <= 256 threads)
+#endif
+__global__ void __launch_bounds__(HK_GENERAL_BOUND, 1) k_general(KParams P, StepIO io, int unlimited, int lanesLog2, int firstClass, int phaseSync, int envWarps, int classWarps) {
   __shared__ Scene S;
   extern __shared__ __align__(16) unsigned char sRaw[];  // phase 2: solve tasks; phase 3: TOI tasks + results (rawBytes())
   stageScene(&S);
@@ -887,7 +896,7 @@ __global__ void __launch_bounds__(kSlowBlock, 1) k_general(KParams P, StepIO io,
 
 #if defined(HK_TU_INLINE)
 }  // namespace
-namespace hkinl {
+namespace HK_INL_NS {
 cudaError_t setScene(const hk::Scene& S) { return cudaMemcpyToSymbol(c_scene, &S, sizeof(Scene)); }
 cudaError_t setMaxDynamicSmem(int bytes) { return cudaFuncSetAttribute(k_general<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); }
 size_t staticSmemGeneral() {
@@ -905,7 +914,7 @@ void launchGeneral1(unsigned grid, int block, size_t smem, cudaStream_t stream, 
 void launchTouch(unsigned grid, int block, cudaStream_t stream, const KParams& P, const hk::StepIO& io) {
   k_touch<<<grid, block, 0, stream>>>(P, io);
 }
-}  // namespace hkinl
+}  // namespace HK_INL_NS
 #else  // pass 1: the rest of the file
 // K fused ticks: body state stays in registers/local memory across ticks, HBM state traffic is paid once
 __global__ void __launch_bounds__(kBlock) k_rollout(KParams P, StepIO io, int k_steps) {
@@ -1303,6 +1312,7 @@ struct hk_env {
     const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
     const int perSmAuto = std::max(1, (targetBlocks + sms - 1) / sms);  // automatic shape: blocks per SM the target asks for
     hkinl::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat * 3));
+    hkinl256::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat * 3));
     cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
     cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
     cudaFuncSetAttribute(k_rollout_fused, cudaFuncAttributePreferredSharedMemoryCarveout, pct(rawBytes(kSlowBlock) + stat + sizeof(FusedShared)));
@@ -1337,8 +1347,9 @@ struct hk_env {
     if (between) between(this, stream, betweenArg);
     const StepIO& iog = ioGeneral ? *ioGeneral : io;
     const int b2 = blockTier2(), w2 = b2 / 32;
-    hkinl::launchGeneral1(gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32), stream, params(), iog,
-                          tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync, envWarps1, classWarps1);
+    (block1 <= 256 ? hkinl256::launchGeneral1 : hkinl::launchGeneral1)(gridSlow(lanes1, envWarps1, classWarps1), block1, rawBytes(envWarps1 * 32),
+                                                                       stream, params(), iog, tiers == 2 ? 1 : 0, lanes1, touch ? 1 : 0, phaseSync,
+                                                                       envWarps1, classWarps1);
     stamp(3, stream);
     if (tiers == 3) k_general<2><<<gridSlow(lanes2, w2), b2, rawBytes(b2), stream>>>(params(), iog, 1, lanes2, 0, phaseSync, w2, 0);
     stamp(4, stream);
@@ -1443,6 +1454,8 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
   cudaError_t err = cudaMemcpyToSymbol(c_scene, &S, sizeof(Scene));
   if (err == cudaSuccess) err = hkinl::setScene(S);
   if (err == cudaSuccess) err = hkinl::setMaxDynamicSmem((int)rawBytes(kSlowBlock));
+  if (err == cudaSuccess) err = hkinl256::setScene(S);
+  if (err == cudaSuccess) err = hkinl256::setMaxDynamicSmem((int)rawBytes(256));
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_general<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_rollout_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rawBytes(kSlowBlock));
   if (err == cudaSuccess) err = cudaMalloc(&h->core, sizeof(float4) * CORE_GROUPS * (size_t)n_envs);

@@ -34,8 +34,15 @@ if a.p2 or not os.path.exists(base2):
     procs.append(subprocess.Popen([nvcc] + hb.NVCC_FLAGS + (["-DHK_TU_INLINE", "-DHK_INLINE_ALL"] + shlex.split(a.p2) if a.p2 != "default" else hb.PASS2_FLAGS) + ["-c", "-o", o2, src]))
 else:
     o2 = base2
-if any(p.wait() for p in procs):
+o3 = os.path.join(hb.OBJ_DIR, f"v_{a.name}_3.o")
+base3 = os.path.join(hb.OBJ_DIR, "hk_inl256.o")
+if a.p2 or not os.path.exists(base3):
+    procs.append(subprocess.Popen([nvcc] + hb.NVCC_FLAGS + (["-DHK_TU_INLINE", "-DHK_INLINE_ALL"] + shlex.split(a.p2) if a.p2 != "default" else hb.PASS2_FLAGS) +
+                                  hb.PASS2B_FLAGS + ["-c", "-o", o3, src]))
+else:
+    o3 = base3
+if any([p.wait() for p in procs]):
     sys.exit("nvcc failed")
 so = os.path.join(hb._ROOT, "build_variants", f"lib_{a.name}.so")
-subprocess.check_call([nvcc] + hb.LINK_FLAGS + ["-o", so, o1, o2])
+subprocess.check_call([nvcc] + hb.LINK_FLAGS + ["-o", so, o1, o2, o3])
 print(so)

@@ -564,7 +564,7 @@ HK_NI_TOI float sepEvaluate(const SepFn& f, const Proxy& pA, const Sweep& sA, co
   }
 }
 
-HK_NI_TOI void timeOfImpact(int* outState, float* outT, const Proxy& proxyA, const Sweep& sweepAin,
+HK_NI_TOIFN void timeOfImpact(int* outState, float* outT, const Proxy& proxyA, const Sweep& sweepAin,
                                  const Proxy& proxyB, const Sweep& sweepBin, float tMax) {
   *outState = TOI_UNKNOWN;
   *outT = tMax;

@@ -64,7 +64,9 @@ __device__ __forceinline__ void loadEnv(const float4* __restrict__ core, int64_t
   F4 g[CORE_GROUPS];
 #pragma unroll
   for (int k = 0; k < CORE_GROUPS; ++k) {
-    float4 v = core[(int64_t)k * n + i];
+    // streaming (evict-first) accesses: at >= 262k envs the state stream would otherwise push the kernels' own code out of
+    // L2 (ncu, k_fast at 1,048,576 envs: 18.6 cycles of no-instruction stall per issued instruction; profiles/README.md)
+    float4 v = __ldcs(&core[(int64_t)k * n + i]);
     g[k] = F4{v.x, v.y, v.z, v.w};
   }
   groupsToEnv(g, e);
@@ -73,7 +75,7 @@ __device__ __forceinline__ void storeEnv(float4* __restrict__ core, int64_t n, i
   F4 g[CORE_GROUPS];
   envToGroups(e, g);
 #pragma unroll
-  for (int k = 0; k < CORE_GROUPS; ++k) core[(int64_t)k * n + i] = make_float4(g[k].x, g[k].y, g[k].z, g[k].w);
+  for (int k = 0; k < CORE_GROUPS; ++k) __stcs(&core[(int64_t)k * n + i], make_float4(g[k].x, g[k].y, g[k].z, g[k].w));
 }
 
 __device__ __forceinline__ void flushInt(double* gstats, int slot, int v, int lane) {
@@ -215,10 +217,18 @@ enum { Q_CLASSES = 4, QC_DONE1 = 4, QC_COUNT2 = 5, QC_DONE2 = 6 };
 // MINB = resident blocks per SM the register allocation aims at: 4 (120 registers, no spills) when the batch is one
 // wave anyway, 5 (96 registers) when occupancy pays (measured: profiles/README.md r1e)
 #if !defined(HK_TU_INLINE)
-template <int MINB>
-__global__ void __launch_bounds__(kBlock, MINB) k_fast(KParams P, StepIO io) {
+// BLOCK = 128: several independent blocks per SM (MINB of them).  BLOCK = kFastWide (batches of >= 200k envs): ONE block per
+// SM whose warps walk the tick in three stages with block barriers in between (controllers | world step | epilogue).
+// A large batch is many waves of blocks, so co-resident 128-thread blocks sit at unrelated places of a 140 KB kernel that
+// has no loops to reuse and every block streams its own instructions from L2 (ncu, 1,048,576 envs: 18.6 cycles of
+// no-instruction stall per issued instruction, 66 % of the kernel; 6.0 at 262,144; 1.7 at 65,536 where the single wave
+// of blocks happens to run in step) -- with one wide block the fetched lines are shared by all the warps of the SM.
+constexpr int kFastWide = 512;
+template <int MINB, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB) k_fast(KParams P, StepIO io) {
+  constexpr bool kStaged = BLOCK > kBlock;
   __shared__ Scene S;
-  __shared__ __align__(16) float sRows[kBlock / 32][32 * 18];  // per warp: its 32 observation rows, staged for 128-bit stores
+  __shared__ __align__(16) float sRows[BLOCK / 32][32 * 18];  // per warp: its 32 observation rows, staged for 128-bit stores
   stageScene(&S);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < P.n;
@@ -228,17 +238,50 @@ __global__ void __launch_bounds__(kBlock, MINB) k_fast(KParams P, StepIO io) {
   int cls = 0;
   const bool stageRows = io.write != 0 && io.stageRows != 0;  // uniform
   float* const myRows = sRows[threadIdx.x >> 5];
-  if (valid) {
+  if (!kStaged) {
+    if (valid) {
+      Env e;
+      loadEnv(P.core, P.n, i, e);
+      e.bailKind = 15;
+      ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st, stageRows ? &wroteFinal : nullptr);
+      if (ok) {
+        storeEnv(P.core, P.n, i, e);
+        if (stageRows) getObs(e, myRows + 18 * (threadIdx.x & 31));
+      } else {
+        tickStatsZero(st);
+        cls = bailClass(e.bailKind);
+      }
+    }
+  } else {  // the same tick (hk_tick.cuh envTickFast), cut at its two call boundaries
     Env e;
-    loadEnv(P.core, P.n, i, e);
-    e.bailKind = 15;
-    ok = envTickFast(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st, stageRows ? &wroteFinal : nullptr);
-    if (ok) {
-      storeEnv(P.core, P.n, i, e);
-      if (stageRows) getObs(e, myRows + 18 * (threadIdx.x & 31));
-    } else {
-      tickStatsZero(st);
-      cls = bailClass(e.bailKind);
+    float a[8];
+    int had1 = 0, had2 = 0;
+    const uint64_t env_id = (uint64_t)(P.env_id_offset + i);
+    if (valid) {
+      loadEnv(P.core, P.n, i, e);
+      e.bailKind = 15;
+      policyActions(P.cfg, e, env_id, io.action ? io.action + (size_t)io.stride * i : nullptr, io.pol1, pol2Of(io, (size_t)i), a);
+      had1 = e.has1;
+      had2 = e.has2;
+    }
+    __syncthreads();
+    if (valid) {
+      ok = envStepFast(S, P.cfg, e, a);
+      if (!ok && io.actBuf) {
+        float4* ab = reinterpret_cast<float4*>(io.actBuf + 8 * i);
+        ab[0] = make_float4(a[0], a[1], a[2], a[3]);
+        ab[1] = make_float4(a[4], a[5], a[6], a[7]);
+      }
+    }
+    __syncthreads();
+    if (valid) {
+      if (ok) {
+        tickFinish(S, P.cfg, e, env_id, (size_t)i, io, io.write != 0, st, had1, had2, stageRows ? &wroteFinal : nullptr);
+        storeEnv(P.core, P.n, i, e);
+        if (stageRows) getObs(e, myRows + 18 * (threadIdx.x & 31));
+      } else {
+        cls = bailClass(e.bailKind);
+      }
     }
   }
   if (stageRows) {  // the warp's envs are consecutive: write its finished rows front to back, 16 bytes per lane
@@ -1301,6 +1344,7 @@ struct hk_env {
   bool carveout = true;
   long long shapeKey() const { return carveout ? ((long long)device << 56) ^ ((long long)block1 << 40) ^ ((long long)classWarps1 << 44) ^ (long long)gridSlow(lanes1, envWarps1, classWarps1) : -2; }
   int fastBlock = kBlock;  // threads per block of k_fast / k_touch (HK_FAST_BLOCK: 32..128)
+  bool fastWide = false;   // k_fast as one staged 512-thread block per SM (HK_FAST_WIDE=0|1; default: from 200k envs)
   size_t staticSmem = sizeof(Scene) + 2048;  // static shared memory of k_general (queried at creation)
   size_t fastSmem = sizeof(Scene) + sizeof(float) * kBlock * 18;  // ... of k_fast
   // The carve-out preference is per-function, process-global state: it is set when a handle is created and again only
@@ -1313,8 +1357,9 @@ struct hk_env {
     const int perSmAuto = std::max(1, (targetBlocks + sms - 1) / sms);  // automatic shape: blocks per SM the target asks for
     hkinl::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat * 3));
     hkinl256::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat * 3));
-    cudaFuncSetAttribute(k_fast<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
-    cudaFuncSetAttribute(k_fast<5>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
+    cudaFuncSetAttribute(k_fast<4, kBlock>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
+    cudaFuncSetAttribute(k_fast<5, kBlock>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
+    cudaFuncSetAttribute(k_fast<1, kFastWide>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(sizeof(Scene) + sizeof(float) * kFastWide * 18 + 1024));
     cudaFuncSetAttribute(k_rollout_fused, cudaFuncAttributePreferredSharedMemoryCarveout, pct(rawBytes(kSlowBlock) + stat + sizeof(FusedShared)));
   }
   // Per-kernel timing (hk_kernel_timing): CUDA events recorded on the launching stream around every kernel of a tick,
@@ -1339,8 +1384,9 @@ struct hk_env {
     }
     if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (20 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
     stamp(0, stream);
-    if (n < 100000) k_fast<4><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
-    else k_fast<5><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    if (fastWide) k_fast<1, kFastWide><<<(unsigned)((n + kFastWide - 1) / kFastWide), kFastWide, 0, stream>>>(params(), io);
+    else if (n < 100000) k_fast<4, kBlock><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
+    else k_fast<5, kBlock><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     stamp(1, stream);
     if (touch) hkinl::launchTouch((unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, stream, params(), io);
     stamp(2, stream);
@@ -1434,13 +1480,15 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
     if (const char* co = getenv("HK_CARVEOUT")) h->carveout = co[0] != '0';
     if (const char* fb = getenv("HK_FAST_BLOCK")) h->fastBlock = std::min(kBlock, std::max(32, atoi(fb) / 32 * 32));
+    h->fastWide = n_envs >= 200000;
+    if (const char* fw = getenv("HK_FAST_WIDE")) h->fastWide = fw[0] == '1';
     h->phaseSync = 31;  // bit 3 (8): pool the single-contact solves too (phase 2); bit 4 (16): re-packed one-point rounds
     if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 31;
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 16) sms = 148;
     cudaFuncAttributes fa;
     h->staticSmem = hkinl::staticSmemGeneral();
-    if (cudaFuncGetAttributes(&fa, k_fast<4>) == cudaSuccess) h->fastSmem = fa.sharedSizeBytes;
+    if (cudaFuncGetAttributes(&fa, k_fast<4, kBlock>) == cudaSuccess) h->fastSmem = fa.sharedSizeBytes;
     h->sms = sms;
     if (const char* f = getenv("HK_FUSED")) h->fused = f[0] != '0';
     if (const char* g = getenv("HK_FUSED_FAST_RUN")) h->fusedFastRun = std::max(1, atoi(g));

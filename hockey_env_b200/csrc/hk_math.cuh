@@ -62,6 +62,16 @@
 #else
 #define HK_NI_POLICY HK_FN_OUTLINE
 #endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_EVALMF)) || defined(HK_IN_EVALMF)
+#define HK_NI_EVALMF HK_FN_INLINE    // evaluateManifold (the manifold routines' common entry: 4 call sites)
+#else
+#define HK_NI_EVALMF HK_FN_OUTLINE
+#endif
+#if (defined(HK_INLINE_ALL) && !defined(HK_OUT_TOIFN)) || defined(HK_IN_TOIFN)
+#define HK_NI_TOIFN HK_FN_INLINE     // b2TimeOfImpact itself (2 call sites; its internals are group TOI)
+#else
+#define HK_NI_TOIFN HK_FN_OUTLINE
+#endif
 #if defined(HK_IN_FASTW1) && !defined(HK_OUT_FASTW1)
 #define HK_NI_FASTW1 HK_FN_INLINE
 #elif defined(HK_OUT_FASTW1)
@@ -88,6 +98,8 @@
 #define HK_HD inline
 #define HK_HD_NOINLINE inline
 #define HK_NI_FASTW inline
+#define HK_NI_EVALMF inline
+#define HK_NI_TOIFN inline
 #define HK_NI_COLLIDE inline
 #define HK_NI_POLICY inline
 #define HK_NI_FASTW1 inline

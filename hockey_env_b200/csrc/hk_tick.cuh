@@ -42,7 +42,7 @@ HK_HD void writeRow18(float* dst, const float* o) {
   // rows are 72 B: 8-byte aligned, so 9 float2 stores
   for (int k = 0; k < 9; ++k) {
 #if defined(__CUDA_ARCH__)
-    reinterpret_cast<float2*>(dst)[k] = make_float2(o[2 * k], o[2 * k + 1]);
+    __stcs(reinterpret_cast<float2*>(dst) + k, make_float2(o[2 * k], o[2 * k + 1]));  // streaming: outputs are not re-read by the kernels
 #else
     dst[2 * k] = o[2 * k];
     dst[2 * k + 1] = o[2 * k + 1];
@@ -52,7 +52,7 @@ HK_HD void writeRow18(float* dst, const float* o) {
 
 HK_HD void writeRow4(float* dst, float a, float b, float c, float d) {  // info rows are 16 B: one 128-bit store
 #if defined(__CUDA_ARCH__)
-  *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+  __stcs(reinterpret_cast<float4*>(dst), make_float4(a, b, c, d));
 #else
   dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
 #endif
@@ -72,9 +72,9 @@ __device__ __forceinline__ void warpStoreRows18(float* __restrict__ dst, const f
     if (j < 144) {
       const bool lo = (mask >> ((4 * j) / 18)) & 1u, hi = (mask >> ((4 * j + 2) / 18)) & 1u;
       const float4 v = reinterpret_cast<const float4*>(stage)[j];
-      if (lo && hi) reinterpret_cast<float4*>(dst)[j] = v;
-      else if (lo) reinterpret_cast<float2*>(dst)[2 * j] = make_float2(v.x, v.y);
-      else if (hi) reinterpret_cast<float2*>(dst)[2 * j + 1] = make_float2(v.z, v.w);
+      if (lo && hi) __stcs(reinterpret_cast<float4*>(dst) + j, v);
+      else if (lo) __stcs(reinterpret_cast<float2*>(dst) + 2 * j, make_float2(v.x, v.y));
+      else if (hi) __stcs(reinterpret_cast<float2*>(dst) + 2 * j + 1, make_float2(v.z, v.w));
     }
   }
 }

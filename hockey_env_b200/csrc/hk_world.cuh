@@ -379,7 +379,7 @@ HK_HD float polyStaticFaceGap(const Scene& S, int f, const Poly& PB, const Xf& x
   return best;
 }
 
-HK_NI_NARROW void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
+HK_NI_EVALMF void evaluateManifold(const Scene& S, const Env& e, int pid, Manifold* m) {
   int fA = S.pairFA[pid], fB = S.pairFB[pid];
   Xf xfA = fixtureXf(S, e, fA);
   if (fB == F_PUCK) {

@@ -343,7 +343,7 @@ def test_pipeline_variants_are_identical(oracle):
     n = 4096
     envs = []
     knobs = ("HK_MONO", "HK_TIERS", "HK_TOUCH", "HK_ENV_WARPS", "HK_SLOW_BLOCK", "HK_CLASS_LANES", "HK_PHASE_SYNC", "HK_CLASS_WARPS",
-             "HK_CARVEOUT", "HK_FAST_BLOCK", "HK_TARGET_BLOCKS")
+             "HK_CARVEOUT", "HK_FAST_BLOCK", "HK_TARGET_BLOCKS", "HK_FAST_WIDE")
     for var in ({"HK_MONO": "1"}, {"HK_TIERS": "2"}, {"HK_TIERS": "3"},
                 # touch tier; 3 env warps + 9 helper warps per block; half-filled warps for two work classes
                 {"HK_TIERS": "2", "HK_TOUCH": "1", "HK_ENV_WARPS": "3", "HK_SLOW_BLOCK": "384", "HK_CLASS_LANES": "5443"},
@@ -352,7 +352,9 @@ def test_pipeline_variants_are_identical(oracle):
                 # blocks cut from the sorted queue (no class-homogeneous shape), one-point pool without re-packed rounds
                 {"HK_CLASS_WARPS": "0", "HK_PHASE_SYNC": "15", "HK_CARVEOUT": "0", "HK_FAST_BLOCK": "64"},
                 # static class shape with single-warp blocks for the TOI-heavy classes
-                {"HK_CLASS_WARPS": "5311"}):
+                {"HK_CLASS_WARPS": "5311"},
+                # the fast tier as one staged 512-thread block per SM (the shape of batches >= 200k envs), with and without touch tier
+                {"HK_FAST_WIDE": "1"}, {"HK_FAST_WIDE": "1", "HK_TOUCH": "1"}):
         old = {k: os.environ.get(k) for k in knobs}
         for k in knobs:
             os.environ.pop(k, None)

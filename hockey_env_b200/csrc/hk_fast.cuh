@@ -211,7 +211,8 @@ HK_NI_FASTW bool worldStepFast(const Scene& S, const Config& cfg, Env& e, float 
 // Collide is the fast one plus an exact update of the puck x racket pairs; the island solve is the general one
 // (hk_world.cuh: one contact, one manifold point -> the register-resident sweep loop, then the position iterations);
 // SolveTOI is replaced by the fast tier's proofs.  Returns false without side effects that matter otherwise.
-HK_HD_NOINLINE bool worldStepTouch(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h) {
+// The touch step in three pieces (k_touch walks them with block barriers in between; worldStepTouch is their sequence).
+HK_HD bool worldStepTouchCollide(const Scene& S, const Config& cfg, const Cache& cache, Env& e) {
   e.enabled = 0xFFFFFFFFu;
   e.nmf = 0;
   e.toiEventSeen = false;
@@ -221,9 +222,14 @@ HK_HD_NOINLINE bool worldStepTouch(const Scene& S, const Config& cfg, const Cach
     e.moved &= ~8u;
     findNewContacts(S, e);
   }
-  if (!collideFast<true>(S, cfg, cache, e)) return false;
+  return collideFast<true>(S, cfg, cache, e);
+}
+HK_HD bool worldStepTouchSolve(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h) {
   solveIslands(S, cfg, cache, e, h, 6 * 30, 2 * 30);
   if (e.aborted) HK_BAIL(11);
+  return true;
+}
+HK_HD bool worldStepTouchFinish(const Scene& S, const Cache& cache, Env& e) {
   uint32_t cand = e.exist & HK_PAIRS_TOI;
   if (cand) {
     for (int i = 0; i < e.ncontacts; ++i) {
@@ -241,6 +247,9 @@ HK_HD_NOINLINE bool worldStepTouch(const Scene& S, const Config& cfg, const Cach
   e.b[0].island = e.b[1].island = e.b[2].island = false;
   worldStepFinish(cache, e);
   return true;
+}
+HK_HD_NOINLINE bool worldStepTouch(const Scene& S, const Config& cfg, const Cache& cache, Env& e, float h) {
+  return worldStepTouchCollide(S, cfg, cache, e) && worldStepTouchSolve(S, cfg, cache, e, h) && worldStepTouchFinish(S, cache, e);
 }
 HK_HD bool envStepTouch(const Scene& S, const Config& cfg, const Cache& cache, Env& e, const float action[8]) {
   envStepActions(S, cfg, e, action);

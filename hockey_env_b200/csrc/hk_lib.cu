@@ -157,6 +157,7 @@ namespace hkinl256 { HK_INL_DECLS }  // pass 2b: k_general<1> bounded to 256 thr
 namespace {
 
 constexpr int kSlowBlock = 384;  // one block per SM at 168 registers: all its warps walk the tick phases together
+constexpr int kTouchBlock = 384; // threads per block of k_touch (pass 2): one block per SM at 166 registers
 
 #if !defined(HK_TU_INLINE)
 __global__ void __launch_bounds__(kBlock) k_create(KParams P) {
@@ -313,37 +314,52 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_fast(KParams P, StepIO io) {
 // Touch tier: work class 0 of k_fast's queue (puck x racket contact ticks, i.e. every keep/shoot tick).  One contact,
 // one manifold point, no continuous-collision event possible -- the lanes of a warp all walk the same short path
 // (hk_fast.cuh worldStepTouch).  Envs whose proofs fail are appended to work class 3 for the general tier.
-__global__ void __launch_bounds__(kBlock) k_touch(KParams P, StepIO io) {
+// One 384-thread block per SM (166 registers), staged like the wide k_fast: actions + Collide | island solve | proofs + epilogue.
+__global__ void __launch_bounds__(kTouchBlock, 1) k_touch(KParams P, StepIO io) {
   __shared__ Scene S;
   stageScene(&S);
   const int lane = threadIdx.x & 31;
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned cnt = *((volatile uint32_t*)&P.qctl[0]);
+  if ((int64_t)blockIdx.x * blockDim.x >= (int64_t)cnt) return;  // block-uniform
   const bool valid = j < (int64_t)cnt;
-  if (!__any_sync(0xffffffffu, valid)) return;
   TickStats st;
   tickStatsZero(st);
-  bool need = false;
+  Env e;
+  Cache cache;
+  float a[8];
+  int had1 = 0, had2 = 0;
   int64_t i = 0;
-  if (valid) {
+  bool live = false;
+  const float h = (float)(1.0 / HK_FPS);
+  if (valid) {  // hk_tick.cuh envTickTouch / hk_fast.cuh envStepTouch, cut at their call boundaries
     i = P.queue[j];
-    Env e;
     loadEnv(P.core, P.n, i, e);
-    Cache cache;
     cache.base = P.cache + i;
     cache.stride = (size_t)P.n;
-    float a[8];
     const float4* ab = reinterpret_cast<const float4*>(io.actBuf + 8 * i);
     float4 lo = ab[0], hi = ab[1];
     a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w; a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
     e.bailKind = 15;
-    if (envTickTouch(S, P.cfg, cache, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st, a)) {
-      storeEnv(P.core, P.n, i, e);
-    } else {
-      tickStatsZero(st);
-      need = true;
-    }
+    policyAdvancePhases(P.cfg, e, (uint64_t)(P.env_id_offset + i), io.pol1, pol2Of(io, (size_t)i));
+    had1 = e.has1;
+    had2 = e.has2;
+    envStepActions(S, P.cfg, e, a);
+    e.sweepBudget = 1 << 20;
+    e.allowToiEvents = true;
+    e.aborted = false;
+    live = worldStepTouchCollide(S, P.cfg, cache, e);
   }
+  __syncthreads();
+  if (live) live = worldStepTouchSolve(S, P.cfg, cache, e, h);
+  __syncthreads();
+  if (live) live = worldStepTouchFinish(S, cache, e);
+  if (live) {
+    envStepAfterWorld(P.cfg, e);
+    tickFinish(S, P.cfg, e, (uint64_t)(P.env_id_offset + i), (size_t)i, io, io.write != 0, st, had1, had2);
+    storeEnv(P.core, P.n, i, e);
+  }
+  const bool need = valid && !live;
   const unsigned m = __ballot_sync(0xffffffffu, need);
   if (m) {
     unsigned base = 0;
@@ -353,7 +369,6 @@ __global__ void __launch_bounds__(kBlock) k_touch(KParams P, StepIO io) {
   }
   flushStats(statsRow(P.stats), st);
 }
-
 #endif  // HK_TU_INLINE
 // Tier 1 and 2 of the cascade run the same general path (hk::envTick) over compacted queues:
 //   TIER == 1 (k_mid): budgeted -- a velocity solve must converge (fixed point / short cycle) within kMidSweeps
@@ -1355,8 +1370,8 @@ struct hk_env {
     const size_t stat = staticSmem;
     const int perSm1 = std::max(1, std::min(65536 / (168 * block1), (int)((gridSlow(lanes1, envWarps1, classWarps1) + 147) / 148)));
     const int perSmAuto = std::max(1, (targetBlocks + sms - 1) / sms);  // automatic shape: blocks per SM the target asks for
-    hkinl::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat * 3));
-    hkinl256::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat * 3));
+    hkinl::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat));
+    hkinl256::setCarveouts(pct((rawBytes(envWarps1 * 32) + stat) * (classWarps1 < 0 ? perSmAuto : perSm1)), pct(stat));
     cudaFuncSetAttribute(k_fast<4, kBlock>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 4));
     cudaFuncSetAttribute(k_fast<5, kBlock>, cudaFuncAttributePreferredSharedMemoryCarveout, pct((fastSmem + 1024) * 5));
     cudaFuncSetAttribute(k_fast<1, kFastWide>, cudaFuncAttributePreferredSharedMemoryCarveout, pct(sizeof(Scene) + sizeof(float) * kFastWide * 18 + 1024));
@@ -1388,7 +1403,7 @@ struct hk_env {
     else if (n < 100000) k_fast<4, kBlock><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     else k_fast<5, kBlock><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     stamp(1, stream);
-    if (touch) hkinl::launchTouch((unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, stream, params(), io);
+    if (touch) hkinl::launchTouch((unsigned)((n + kTouchBlock - 1) / kTouchBlock), kTouchBlock, stream, params(), io);
     stamp(2, stream);
     if (between) between(this, stream, betweenArg);
     const StepIO& iog = ioGeneral ? *ioGeneral : io;

@@ -218,7 +218,7 @@ enum { Q_CLASSES = 4, QC_DONE1 = 4, QC_COUNT2 = 5, QC_DONE2 = 6 };
 // MINB = resident blocks per SM the register allocation aims at: 4 (120 registers, no spills) when the batch is one
 // wave anyway, 5 (96 registers) when occupancy pays (measured: profiles/README.md r1e)
 #if !defined(HK_TU_INLINE)
-// BLOCK = 128: several independent blocks per SM (MINB of them).  BLOCK = kFastWide (batches of >= 200k envs): ONE block per
+// BLOCK = 128: several independent blocks per SM (MINB of them).  BLOCK = kFastWide (batches of >= 120k envs): ONE block per
 // SM whose warps walk the tick in three stages with block barriers in between (controllers | world step | epilogue).
 // A large batch is many waves of blocks, so co-resident 128-thread blocks sit at unrelated places of a 140 KB kernel that
 // has no loops to reuse and every block streams its own instructions from L2 (ncu, 1,048,576 envs: 18.6 cycles of
@@ -1359,7 +1359,7 @@ struct hk_env {
   bool carveout = true;
   long long shapeKey() const { return carveout ? ((long long)device << 56) ^ ((long long)block1 << 40) ^ ((long long)classWarps1 << 44) ^ (long long)gridSlow(lanes1, envWarps1, classWarps1) : -2; }
   int fastBlock = kBlock;  // threads per block of k_fast / k_touch (HK_FAST_BLOCK: 32..128)
-  bool fastWide = false;   // k_fast as one staged 512-thread block per SM (HK_FAST_WIDE=0|1; default: from 200k envs)
+  bool fastWide = false;   // k_fast as one staged 512-thread block per SM (HK_FAST_WIDE=0|1; default: from 120k envs)
   size_t staticSmem = sizeof(Scene) + 2048;  // static shared memory of k_general (queried at creation)
   size_t fastSmem = sizeof(Scene) + sizeof(float) * kBlock * 18;  // ... of k_fast
   // The carve-out preference is per-function, process-global state: it is set when a handle is created and again only
@@ -1495,7 +1495,7 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
     if (const char* co = getenv("HK_CARVEOUT")) h->carveout = co[0] != '0';
     if (const char* fb = getenv("HK_FAST_BLOCK")) h->fastBlock = std::min(kBlock, std::max(32, atoi(fb) / 32 * 32));
-    h->fastWide = n_envs >= 200000;
+    h->fastWide = n_envs >= 120000;  // measured (profiles/README.md r3d, r3f): -45 % at 1,048,576 envs, -12 % at 262,144, -3 % at 131,072, +10 % at 98,304
     if (const char* fw = getenv("HK_FAST_WIDE")) h->fastWide = fw[0] == '1';
     h->phaseSync = 31;  // bit 3 (8): pool the single-contact solves too (phase 2); bit 4 (16): re-packed one-point rounds
     if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 31;

@@ -218,7 +218,7 @@ enum { Q_CLASSES = 4, QC_DONE1 = 4, QC_COUNT2 = 5, QC_DONE2 = 6 };
 // MINB = resident blocks per SM the register allocation aims at: 4 (120 registers, no spills) when the batch is one
 // wave anyway, 5 (96 registers) when occupancy pays (measured: profiles/README.md r1e)
 #if !defined(HK_TU_INLINE)
-// BLOCK = 128: several independent blocks per SM (MINB of them).  BLOCK = kFastWide (batches of >= 120k envs): ONE block per
+// BLOCK = 128: several independent blocks per SM (MINB of them).  BLOCK = kFastWide (batches of >= 16k envs): ONE block per
 // SM whose warps walk the tick in three stages with block barriers in between (controllers | world step | epilogue).
 // A large batch is many waves of blocks, so co-resident 128-thread blocks sit at unrelated places of a 140 KB kernel that
 // has no loops to reuse and every block streams its own instructions from L2 (ncu, 1,048,576 envs: 18.6 cycles of
@@ -1359,7 +1359,8 @@ struct hk_env {
   bool carveout = true;
   long long shapeKey() const { return carveout ? ((long long)device << 56) ^ ((long long)block1 << 40) ^ ((long long)classWarps1 << 44) ^ (long long)gridSlow(lanes1, envWarps1, classWarps1) : -2; }
   int fastBlock = kBlock;  // threads per block of k_fast / k_touch (HK_FAST_BLOCK: 32..128)
-  bool fastWide = false;   // k_fast as one staged 512-thread block per SM (HK_FAST_WIDE=0|1; default: from 120k envs)
+  bool fastWide = false;   // k_fast as one staged 512-thread block per SM (HK_FAST_WIDE=0|1; default: from 16k envs)
+  int fastWideBlock = kFastWide;  // its threads per block: the batch cut into whole waves of one block per SM (<= 512 threads)
   size_t staticSmem = sizeof(Scene) + 2048;  // static shared memory of k_general (queried at creation)
   size_t fastSmem = sizeof(Scene) + sizeof(float) * kBlock * 18;  // ... of k_fast
   // The carve-out preference is per-function, process-global state: it is set when a handle is created and again only
@@ -1399,7 +1400,7 @@ struct hk_env {
     }
     if (trace) cudaMemsetAsync(trace, 0, sizeof(uint32_t) * (20 * ((size_t)n / 32 + 8) + 2 * (size_t)n), stream);
     stamp(0, stream);
-    if (fastWide) k_fast<1, kFastWide><<<(unsigned)((n + kFastWide - 1) / kFastWide), kFastWide, 0, stream>>>(params(), io);
+    if (fastWide) k_fast<1, kFastWide><<<(unsigned)((n + fastWideBlock - 1) / fastWideBlock), fastWideBlock, 0, stream>>>(params(), io);
     else if (n < 100000) k_fast<4, kBlock><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     else k_fast<5, kBlock><<<(unsigned)((n + fastBlock - 1) / fastBlock), fastBlock, 0, stream>>>(params(), io);
     stamp(1, stream);
@@ -1495,12 +1496,20 @@ int hk_create(hk_env** out, int64_t n_envs, int mode, int keep_mode, int device,
     if (tt && (tt[0] == '0' || tt[0] == '1')) h->touch = tt[0] == '1';
     if (const char* co = getenv("HK_CARVEOUT")) h->carveout = co[0] != '0';
     if (const char* fb = getenv("HK_FAST_BLOCK")) h->fastBlock = std::min(kBlock, std::max(32, atoi(fb) / 32 * 32));
-    h->fastWide = n_envs >= 120000;  // measured (profiles/README.md r3d, r3f): -45 % at 1,048,576 envs, -12 % at 262,144, -3 % at 131,072, +10 % at 98,304
+    // measured (profiles/README.md r3d, r3f, r3k): with the block size fitted to whole waves the staged shape wins at every size
+    // from 16k envs (-4 % at 16k, -8 % at 32k, -2 % at 65k, -5 % at 131k, -10 % at 262k, -45 % at 1,048,576)
+    h->fastWide = n_envs >= 16000;
     if (const char* fw = getenv("HK_FAST_WIDE")) h->fastWide = fw[0] == '1';
     h->phaseSync = 31;  // bit 3 (8): pool the single-contact solves too (phase 2); bit 4 (16): re-packed one-point rounds
     if (const char* ps = getenv("HK_PHASE_SYNC")) h->phaseSync = atoi(ps) & 31;
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms < 16) sms = 148;
+    {  // wide k_fast: w = ceil(n / (sms * 512)) waves of one block per SM, block = ceil(n / (sms * w)) rounded up to a warp
+      const int64_t waves = (n_envs + (int64_t)sms * kFastWide - 1) / ((int64_t)sms * kFastWide);
+      const int64_t per = (n_envs + sms * waves - 1) / (sms * waves);
+      h->fastWideBlock = (int)std::min<int64_t>(kFastWide, std::max<int64_t>(128, (per + 31) / 32 * 32));
+      if (const char* fb = getenv("HK_FAST_WIDE_BLOCK")) h->fastWideBlock = std::min(kFastWide, std::max(32, atoi(fb) / 32 * 32));
+    }
     cudaFuncAttributes fa;
     h->staticSmem = hkinl::staticSmemGeneral();
     if (cudaFuncGetAttributes(&fa, k_fast<4, kBlock>) == cudaSuccess) h->fastSmem = fa.sharedSizeBytes;

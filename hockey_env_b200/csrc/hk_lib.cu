@@ -370,13 +370,13 @@ __global__ void __launch_bounds__(kTouchBlock, 1) k_touch(KParams P, StepIO io) 
   flushStats(statsRow(P.stats), st);
 }
 #endif  // HK_TU_INLINE
-// Tier 1 and 2 of the cascade run the same general path (hk::envTick) over compacted queues:
-//   TIER == 1 (k_mid): budgeted -- a velocity solve must converge (fixed point / short cycle) within kMidSweeps
-//                      sweeps and no continuous-collision EVENT may occur; otherwise the env is appended to the
-//                      tier-2 queue with nothing committed.  Its queue is sorted by work class and every class
-//                      starts on a warp boundary, so the 32 lanes of a warp do the same kind of tick.
-//   TIER == 2 (k_long): unlimited.  Its lanes are the rare long solves and TOI events, packed densely, instead
-//                      of each of them stalling 31 converged neighbours for up to 180 sweeps.
+// The general tier(s) run the same general path (generalTick below) over the class-sorted queue of k_fast:
+//   k_general<1>, unlimited = 1 (the default, HK_TIERS=2): every queued env finishes its tick here.
+//   k_general<1>, unlimited = 0 + k_general<2> (HK_TIERS=3; built and parity-tested, not the default at any batch size):
+//                      tier 1 is budgeted -- a velocity solve must converge (fixed point / short cycle) within kMidSweeps
+//                      sweeps and no continuous-collision EVENT may occur; otherwise the env is appended to the tier-2
+//                      queue with nothing committed, and k_general<2> redoes its tick without limits, packed densely.
+//   Every work class starts on a warp boundary, so the 32 lanes of a warp do the same kind of tick.
 constexpr int kMidSweeps = 24;
 // Velocity solves of a block are pooled in shared memory (phase 2 of k_general) and dealt to its warps as units of one
 // loop shape each: a warp never runs two different 180-sweep loops one after the other unless the block holds more

@@ -53,6 +53,8 @@ CONFIGS = {
                             text="65536 TRAIN_DEFENSE envs per GPU, strong vs weak BasicOpponent"),
     "normal1M": dict(mode="NORMAL", p1="strong", p2="strong", per_gpu=None, total=1048576,
                      text="1048576 NORMAL envs in total, strong-vs-strong in-kernel BasicOpponent"),
+    "normal1M_weak": dict(mode="NORMAL", p1="weak", p2="strong", per_gpu=None, total=1048576,
+                          text="1048576 NORMAL envs in total, weak-vs-strong in-kernel BasicOpponent"),
     "actor262k": dict(mode="NORMAL", p1="actor", p2="strong", per_gpu=None, total=262144,
                       text="262144 NORMAL envs in total, player 1 = TD3 actor (stage_3 weights, on device), player 2 = "
                            "in-kernel strong BasicOpponent"),

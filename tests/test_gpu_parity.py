@@ -58,6 +58,38 @@ def test_fused_policies_full_state_parity(oracle, mode, p1, p2, steps):
     assert s["episodes"] > 0
 
 
+@pytest.mark.parametrize("n,mode,p1,p2,steps,touch", [
+    (16384, 0, 2, 2, 120, "0"),   # the staged one-block-per-SM fast tier (>= 16k envs) + 256-thread general blocks
+    (32768, 2, 2, 1, 60, "0"),    # TRAIN_DEFENSE at a size where general blocks are full
+    (16384, 0, 2, 2, 120, "1"),   # ... with the staged touch tier forced on (the shape of batches >= 750k envs)
+])
+def test_large_batch_kernel_shapes_parity(oracle, n, mode, p1, p2, steps, touch):
+    """The kernel shapes that only large batches select (wide staged k_fast, full general blocks, staged k_touch) against
+    the oracle: every output every tick, the full state record at the end."""
+    import os
+    import hockey_env_b200 as hk
+    from parity_util import state_mismatches
+    O = oracle
+    old = os.environ.get("HK_TOUCH")
+    os.environ["HK_TOUCH"] = touch
+    try:
+        env, ora = _mk(hk, O, n, mode, 900 + mode, p1, p2, env_id_offset=7_000_000_000)
+    finally:
+        os.environ.pop("HK_TOUCH", None)
+        if old is not None:
+            os.environ["HK_TOUCH"] = old
+    for t in range(steps):
+        env.step()
+        ro = ora.step(None, p1, p2, O.STEP_AUTORESET)
+        _compare_step(env, ro, t)
+    bad = state_mismatches(ora.get_state(), _state(env))
+    assert len(bad) == 0, f"state differs: {bad[:8].tolist()}"
+    s, so = env.stats(), ora.stats()
+    assert s["overflows"] == 0 and s["episodes"] > 0
+    for k, i in (("episodes", 0), ("wins", 1), ("losses", 2), ("draws", 3), ("env_steps", 4), ("toi_events", 12)):
+        assert s[k] == so[i], k
+
+
 def test_external_actions_and_no_autoreset(oracle):
     """HockeyEnv.step with caller-supplied [N,8] actions (incl. values outside [-1,1], clipped as hockey_env.py:659)
     and stepping after done (the reference has no guard)."""
